@@ -1,0 +1,160 @@
+/*
+ * shdr.h -- C ABI of libshdr.so: the B200-native (sm_100a) Linearization-Net
+ * per-pixel path of SingleHDR-tf2.
+ *
+ * The reference (ShinYwings/SingleHDR-tf2) has no FFI/plugin layer: its
+ * boundary for this path is the Python call surface of a Keras Model and a
+ * utility module.  Each entry point below is the native replacement for one
+ * of those Python functions; the Python shims that keep the reference's names
+ * and argument meaning live in singlehdr-tf2_b200/layers.py, and the
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / TF types.
+ *   - Every tensor is float32, NHWC, compact row-major.
+ *   - Device-pointer entry points are ASYNCHRONOUS on `stream` (a cudaStream_t
+ *     cast to void*; NULL = legacy default stream) on the device that owns
+ *     `out`; the caller owns every buffer and nothing is retained after return.
+ *   - Return value: SHDR_OK (0) or a negative SHDR_ERR_* code; the message is
+ *     available from shdr_last_error() (thread-local).
+ *   - Re-entrant and thread-safe; the only global state is the EMoR table.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry
+ *     point returns SHDR_ERR_CUDA.
+ */
+#ifndef SHDR_H_
+#define SHDR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHDR_VERSION 100            /* 0.1.0 */
+
+#define SHDR_OK               0
+#define SHDR_ERR_INVALID     -1     /* bad argument (shape, NULL pointer, alignment ...) */
+#define SHDR_ERR_CUDA        -2     /* CUDA runtime error (message has cudaGetErrorString) */
+#define SHDR_ERR_UNSUPPORTED -3     /* valid request this build does not implement */
+#define SHDR_ERR_NOTABLE     -4     /* EMoR table needed but shdr_set_emor_table not called */
+
+#define SHDR_EMOR_SAMPLES   1024    /* linearization_net.py:181 */
+#define SHDR_EMOR_NCOMP       11    /* linearization_net.py:182,225 */
+#define SHDR_FRONTEND_CH      93    /* 3 img + 6 edge + 12 + 24 + 48, linearization_net.py:322 */
+#define SHDR_HIST_CH          84    /* 12 + 24 + 48 */
+
+int         shdr_version(void);
+const char* shdr_last_error(void);
+/* number of visible CUDA devices (0 and SHDR_OK when the driver is absent) */
+int         shdr_device_count(int* count);
+
+/* ---- EMoR inverse table ------------------------------------------------
+ * Replaces the per-call text parse inside AEInvcrfDecodeNet.invcrf_pca_w_2_invcrf
+ * (linearization_net.py:233 -> parse_invemor :217-227).  g0_host[s], hinv_host is
+ * [s][ncomp] row-major (what parse_invemor's np.stack(..., axis=-1) returns).
+ * Host copy is kept; each device gets its copy on first use.  s must be 1024 and
+ * ncomp 11 in this build. */
+int shdr_set_emor_table(const float* g0_host, const float* hinv_host, int s, int ncomp);
+
+/* ---- (A) feature front end ---------------------------------------------- */
+
+/* tf.image.sobel_edges(img) reshaped to [n,h,w,2c]  (linearization_net.py:312-314):
+ * REFLECT pad 1, channel = c*2 + k, k=0 dy, k=1 dx.  h,w >= 2.
+ * Output pixel p, channel j is written to out[p*out_ch_stride + out_ch_off + j]
+ * (out_ch_stride = 2c, out_ch_off = 0 for a stand-alone tensor). */
+int shdr_sobel6_f32(const float* img, float* out, int n, int h, int w, int c,
+                    int out_ch_stride, int out_ch_off, void* stream);
+
+/* model.histogram_layer(img, bins)  (linearization_net.py:336-350), optionally fused
+ * with the 16x16 / stride 1 / 'same' average pool of :351 (pool_k = 0 or 16; the
+ * pooled form needs c == 3).  Output channel = (bin-1)*c + ch, written with the same
+ * out_ch_stride / out_ch_off rule as above (stride = c*bins for stand-alone). */
+int shdr_soft_hist_f32(const float* img, float* out, int n, int h, int w, int c,
+                       int bins, int pool_k, int out_ch_stride, int out_ch_off,
+                       void* stream);
+
+/* concat(histogram_layer(img,4), (img,8), (img,16)) -> out[n,h,w,84], one launch,
+ * pool_k = 0 | 16.  img is [n,h,w,3]. */
+int shdr_hist_multi_f32(const float* img, float* out, int n, int h, int w,
+                        int pool_k, void* stream);
+
+/* The whole front end of linearization_net.model.call (:312-322):
+ * out[n,h,w,93] = concat(img, edge6, hist4, hist8, hist16); pool_k = 0 (as shipped
+ * by the reference) or 16 (histograms pooled). */
+int shdr_frontend_f32(const float* img, float* out, int n, int h, int w,
+                      int pool_k, void* stream);
+
+/* ---- (B) inverse-CRF stage ----------------------------------------------- */
+
+/* AEInvcrfDecodeNet.invcrf_pca_w_2_invcrf (:231-253): curve[b,1024] = g0 + hinv.w[b,11];
+ * monotone != 0 additionally applies model._increase (:368-392). */
+int shdr_invcrf_build_f32(const float* w, float* curve, int b, int monotone, void* stream);
+
+/* model._increase(rf) (:368-392) on rf[b,k], 2 <= k <= 65536. */
+int shdr_increase_f32(const float* rf, float* out, int b, int k, void* stream);
+
+/* tf_utils.apply_rf(x, rf) (tf_utils.py:95-105): x[b, elems_per_item], rf[b,k]. */
+int shdr_apply_rf_f32(const float* x, const float* rf, float* y, int b,
+                      long long elems_per_item, int k, void* stream);
+
+/* PCA build + _increase + apply_rf back to back on `stream` (what the inference
+ * graph does at test_real_refinement.py:94-95).  curve_out[b,1024] is a required
+ * scratch/output buffer. */
+int shdr_linearize_f32(const float* x, const float* w, float* y, float* curve_out,
+                       int b, long long elems_per_item, void* stream);
+
+/* ---- DLPack entry points ------------------------------------------------------
+ * Same operations on DLManagedTensor* (DLPack v0.x ABI, as produced by
+ * tf.experimental.dlpack.to_dlpack / torch.utils.dlpack.to_dlpack).  Inputs are
+ * validated (kDLCUDA, float32, lanes 1, compact row-major or NULL strides) and never
+ * written or consumed (the caller still owns the capsule).  Outputs are allocated by
+ * the library on the inputs' device and returned as a new DLManagedTensor whose
+ * deleter frees the device memory -- wrap it in a "dltensor" capsule and hand it to
+ * from_dlpack. */
+struct DLManagedTensor;
+int shdr_dl_frontend(const struct DLManagedTensor* img, int pool_k, void* stream,
+                     struct DLManagedTensor** out);
+int shdr_dl_sobel6(const struct DLManagedTensor* img, void* stream,
+                   struct DLManagedTensor** out);
+int shdr_dl_soft_hist(const struct DLManagedTensor* img, int bins, int pool_k,
+                      void* stream, struct DLManagedTensor** out);
+int shdr_dl_invcrf_build(const struct DLManagedTensor* w, int monotone, void* stream,
+                         struct DLManagedTensor** out);
+int shdr_dl_increase(const struct DLManagedTensor* rf, void* stream,
+                     struct DLManagedTensor** out);
+int shdr_dl_apply_rf(const struct DLManagedTensor* x, const struct DLManagedTensor* rf,
+                     void* stream, struct DLManagedTensor** out);
+/* allocate an uninitialised float32 CUDA tensor (for callers that build their own) */
+int shdr_dl_alloc_f32(const int64_t* shape, int ndim, int device,
+                      struct DLManagedTensor** out);
+/* run the deleter of a tensor returned above that was never handed to a consumer */
+void shdr_dl_release(struct DLManagedTensor* t);
+/* address of a `void (*)(PyObject*)` usable as PyCapsule destructor for a "dltensor" capsule:
+ * it runs the tensor's deleter unless a consumer renamed the capsule ("used_dltensor"). */
+void* shdr_dl_capsule_destructor(void);
+
+/* ---- TF-free / torch-free device helpers (tests, bench, host-buffer API) ------- */
+int shdr_malloc(void** p, size_t bytes, int device);
+int shdr_free(void* p, int device);
+int shdr_malloc_host(void** p, size_t bytes);              /* pinned */
+int shdr_free_host(void* p);
+int shdr_memset(void* p, int value, size_t bytes, int device, void* stream);
+int shdr_h2d(void* dst_dev, const void* src_host, size_t bytes, int device, void* stream);
+int shdr_d2h(void* dst_host, const void* src_dev, size_t bytes, int device, void* stream);
+int shdr_sync(int device);                                 /* cudaDeviceSynchronize */
+int shdr_stream_create(void** stream, int device);         /* non-blocking stream */
+int shdr_stream_destroy(void* stream, int device);
+int shdr_stream_sync(void* stream, int device);
+int shdr_event_create(void** event, int device);
+int shdr_event_destroy(void* event, int device);
+int shdr_event_record(void* event, void* stream, int device);
+int shdr_event_elapsed_ms(void* start, void* stop, float* ms);   /* syncs on stop */
+int shdr_stream_wait_event(void* stream, void* event, int device);
+/* number of kernels this library has launched in this process (all threads) */
+long long shdr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHDR_H_ */

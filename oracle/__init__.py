@@ -1,0 +1,27 @@
+"""CPU oracle for the Linearization-Net per-pixel path -- TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: the reference (ShinYwings/SingleHDR-tf2) delegates every
+arithmetic step of this path to TensorFlow >= 2.4 (un-vendored, unpinned,
+``README.md:100``), TensorFlow cannot be installed in the build image, and the
+reference ships no tests, golden vectors or fixtures.  The oracle therefore
+restates the reference's Python op-for-op (same fp32 rounding points, same op
+order) from the call sites cited in every function, and is anchored on
+
+* the known-answer material the reference does hold (``figure/lin2.png`` B=5
+  soft-histogram example; structural facts of ``invemor.txt``), and
+* two independent cross-checks: an fp64 "truth" evaluation of the same
+  formulas, and stock CPU PyTorch ops with the same published semantics
+  (reflect-pad depthwise conv, ``avg_pool2d(count_include_pad=False)``,
+  ``cumsum``) -- see ``tests/test_oracle.py``.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs may import this package.  The product package
+(``singlehdr-tf2_b200``) never does: it fails loudly when its CUDA library is
+missing instead of falling back to anything here.
+"""
+from .np_oracle import (  # noqa: F401
+    BINS, S, NCOMP,
+    sobel_edges6, histogram_layer, avg_pool_same, frontend, hist_multi,
+    parse_invemor, parse_table, invcrf_pca_w_2_invcrf, increase, apply_rf,
+    linearize, hist_centers,
+)

@@ -1,0 +1,222 @@
+"""NumPy restatement of the reference's Linearization-Net per-pixel path.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``) -- PARITY UNPINNED.
+
+Every function mirrors the reference op-for-op: one NumPy full-tensor op per
+TensorFlow op, in the same order, rounding to ``dtype`` (float32 by default) at
+the same points.  Passing ``dtype=np.float64`` evaluates the same formulas in
+double precision with double-precision constants (the "truth" the fp32 paths
+are compared with).  [TF-sem] marks TensorFlow semantics that are not visible
+in ``/root/reference`` (TensorFlow itself is not vendored there).
+
+All ``file:line`` citations are into the reference repository
+(ShinYwings/SingleHDR-tf2).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+BINS = (4, 8, 16)   # linearization_net.py:322
+S = 1024            # linearization_net.py:181   samples per curve
+NCOMP = 11          # linearization_net.py:182,225  PCA components used
+
+
+# --------------------------------------------------------------------------
+# (A) feature front end
+# --------------------------------------------------------------------------
+def _reflect_pad1(img):
+    """tf.pad(img, [[0,0],[1,1],[1,1],[0,0]], 'REFLECT') [TF-sem]: index -1 -> 1,
+    h -> h-2 (no edge repeat).  Requires h >= 2 and w >= 2."""
+    if img.shape[1] < 2 or img.shape[2] < 2:
+        raise ValueError("REFLECT pad needs h >= 2 and w >= 2")
+    return np.pad(img, ((0, 0), (1, 1), (1, 1), (0, 0)), mode="reflect")
+
+
+# tap order = row-major over the 3x3 filter, as a depthwise VALID correlation
+# accumulates it [TF-sem]; products with +-1, +-2, 0 are exact in fp32.
+_KY = ((-1.0, -2.0, -1.0), (0.0, 0.0, 0.0), (1.0, 2.0, 1.0))   # d/dy
+_KX = ((-1.0, 0.0, 1.0), (-2.0, 0.0, 2.0), (-1.0, 0.0, 1.0))   # d/dx
+
+
+def sobel_edges6(img, dtype=np.float32):
+    """``tf.image.sobel_edges(img)`` reshaped to 6 channels.
+
+    linearization_net.py:312-314.  Output channel ``c*2 + k`` with k=0 -> dy,
+    k=1 -> dx (the ``[b,h,w,3,2]`` tensor flattened row-major).
+    """
+    img = np.asarray(img, dtype=dtype)
+    n, h, w, c = img.shape
+    p = _reflect_pad1(img)
+    out = np.empty((n, h, w, c, 2), dtype=dtype)
+    for k, ker in enumerate((_KY, _KX)):
+        acc = np.zeros((n, h, w, c), dtype=dtype)
+        for r in range(3):
+            for s in range(3):
+                wt = ker[r][s]
+                if wt == 0.0:
+                    continue  # + 0*x is exact; skipping keeps the order of the rest
+                acc = acc + dtype(wt) * p[:, r:r + h, s:s + w, :]
+        out[..., k] = acc
+    return out.reshape(n, h, w, c * 2)
+
+
+def hist_centers(max_bin, dtype=np.float32):
+    """Bin centres ``tf.divide(2.*i - 1., 2.*max_bin)`` for i = 1..max_bin.
+
+    linearization_net.py:342,345.  [TF-sem] both Python floats become float32
+    tensors, so the quotient is an fp32 division.
+    """
+    i = np.arange(1, max_bin + 1)
+    return (2.0 * i - 1.0).astype(dtype) / dtype(2.0 * max_bin)
+
+
+def histogram_layer(img, max_bin, dtype=np.float32):
+    """``model.histogram_layer(img, max_bin)``, linearization_net.py:336-350.
+
+    Per bin i=1..B: d=|img - (2i-1)/(2B)|; h = (d < 1/B) ? 1 - d*B : 0; bins
+    concatenated on the channel axis (channel = (i-1)*C + c).
+    """
+    img = np.asarray(img, dtype=dtype)
+    threshold = dtype(1.0 / max_bin)            # :339  python double -> tensor dtype
+    centers = hist_centers(max_bin, dtype)      # :342,345
+    bins = []
+    for i in range(max_bin):                    # :344
+        distance = np.abs(img - centers[i])     # :345
+        histo = np.where(distance < threshold,  # :346  tf.less is strict
+                         dtype(1.0) - distance * dtype(max_bin),
+                         dtype(0.0))
+        bins.append(histo.astype(dtype))
+    return np.concatenate(bins, axis=-1)        # :349
+
+
+def avg_pool_same(x, k=16, dtype=np.float32):
+    """``average_pooling2d(x, k, 1, 'same')`` -- the optional pool of
+    linearization_net.py:351 (dead code there; README.md:51).
+
+    [TF-sem] SAME pads (k-1)//2 before and the rest after; the average divides
+    by the number of in-bounds elements; the CPU kernel accumulates a window
+    in input raster order.  Zero padding is used here only as an exact no-op
+    (x + 0.0 == x), so the accumulation order over valid elements is raster.
+    """
+    x = np.asarray(x, dtype=dtype)
+    n, h, w, c = x.shape
+    pb = (k - 1) // 2
+    pa = k - 1 - pb
+    p = np.pad(x, ((0, 0), (pb, pa), (pb, pa), (0, 0)))
+    acc = np.zeros_like(x)
+    for dy in range(k):
+        for dx in range(k):
+            acc += p[:, dy:dy + h, dx:dx + w, :]
+    ys = np.arange(h)
+    xs = np.arange(w)
+    cy = np.minimum(ys + pa, h - 1) - np.maximum(ys - pb, 0) + 1
+    cx = np.minimum(xs + pa, w - 1) - np.maximum(xs - pb, 0) + 1
+    cnt = (cy[:, None] * cx[None, :]).astype(dtype)
+    return (acc / cnt[None, :, :, None]).astype(dtype)
+
+
+def hist_multi(img, bins=BINS, pool_k=0, dtype=np.float32):
+    """concat of ``histogram_layer(img, B)`` for B in ``bins`` (each optionally
+    pooled), linearization_net.py:322 minus the img/edge pieces."""
+    parts = []
+    for b in bins:
+        hst = histogram_layer(img, b, dtype)
+        if pool_k:
+            hst = avg_pool_same(hst, pool_k, dtype)
+        parts.append(hst)
+    return np.concatenate(parts, axis=-1)
+
+
+def frontend(img, bins=BINS, pool_k=0, dtype=np.float32):
+    """The 93-channel tensor fed to ``crfFeatureNet``:
+    ``concat([img, edge6, hist4, hist8, hist16], -1)``, linearization_net.py:312-322."""
+    img = np.asarray(img, dtype=dtype)
+    return np.concatenate(
+        [img, sobel_edges6(img, dtype), hist_multi(img, bins, pool_k, dtype)], axis=-1)
+
+
+# --------------------------------------------------------------------------
+# (B) inverse-CRF stage
+# --------------------------------------------------------------------------
+def _parse(lines, tag):
+    """``AEInvcrfDecodeNet._parse``, linearization_net.py:255-268: 256 lines of
+    four tokens after the line equal to ``tag``."""
+    for line_idx, line in enumerate(lines):
+        if line == tag:
+            break
+    else:
+        raise ValueError(f"tag {tag!r} not found")
+    r = []
+    for idx in range(line_idx + 1, line_idx + 1 + 256):
+        r += lines[idx].split()
+    return np.float32(r)
+
+
+def parse_invemor(path="invemor.txt"):
+    """``AEInvcrfDecodeNet.parse_invemor``, linearization_net.py:217-227.
+    Returns (B[1024], g0[1024], hinv[1024,11]) float32."""
+    with open(os.path.join(path), "r") as f:
+        lines = [line.strip() for line in f.readlines()]
+    b = _parse(lines, "B =")
+    g0 = _parse(lines, "g0 =")
+    hinv = np.stack([_parse(lines, f"hinv({i + 1})=") for i in range(NCOMP)], axis=-1)
+    return b, g0, hinv
+
+
+parse_table = parse_invemor
+
+
+def invcrf_pca_w_2_invcrf(w, g0, hinv, dtype=np.float32):
+    """``AEInvcrfDecodeNet.invcrf_pca_w_2_invcrf``, linearization_net.py:231-253:
+    ``g0 + matmul(tile(hinv)[b,s,11], w[b,11,1])`` squeezed to [b,s]."""
+    w = np.asarray(w, dtype=dtype)
+    b = w.shape[0]
+    g0_ = np.asarray(g0, dtype=dtype).reshape(1, -1, 1)                 # :239
+    h_ = np.tile(np.asarray(hinv, dtype=dtype)[None], (b, 1, 1))        # :241-243
+    inv = g0_ + np.matmul(h_, w[:, :, None])                            # :246-249
+    return inv[..., 0].astype(dtype)                                    # :251
+
+
+def increase(rf, dtype=np.float32):
+    """``model._increase``, linearization_net.py:368-392."""
+    rf = np.asarray(rf, dtype=dtype)
+    g = rf[:, 1:] - rf[:, :-1]                                  # :370
+    min_g = np.min(g, axis=-1, keepdims=True)                   # :373
+    r = np.maximum(-min_g, dtype(0.0))                          # :377 relu(-min)
+    new_g = g + r                                               # :380
+    with np.errstate(invalid="ignore", divide="ignore"):
+        new_g = new_g / np.sum(new_g, axis=-1, keepdims=True, dtype=dtype)   # :383
+    new_rf = np.cumsum(new_g, axis=-1, dtype=dtype)             # :386 inclusive, sequential
+    return np.pad(new_rf, ((0, 0), (1, 0))).astype(dtype)       # :389
+
+
+def apply_rf(x, rf, dtype=np.float32):
+    """``tf_utils.apply_rf`` -> ``interp_1d`` -> ``sample_1d``,
+    tf_utils.py:95-105, 70-93, 54-68."""
+    x = np.asarray(x, dtype=dtype)
+    rf = np.asarray(rf, dtype=dtype)
+    b = x.shape[0]
+    k = rf.shape[1]
+    y = dtype(k - 1) * x.reshape(b, -1)                         # :103
+    y_0 = np.floor(y)                                           # :77
+    y_1 = y_0 + dtype(1.0)                                      # :78
+    with np.errstate(invalid="ignore"):
+        i0 = np.clip(y_0.astype(np.int32), 0, k - 1)            # :82,66
+        i1 = np.clip(y_1.astype(np.int32), 0, k - 1)
+    rows = np.arange(b)[:, None]                                # :61-63
+    v0 = rf[rows, i0]                                           # :68 gather_nd
+    v1 = rf[rows, i1]
+    w_0 = y_1 - y                                               # :87
+    w_1 = y - y_0                                               # :88
+    out = w_0 * v0 + w_1 * v1                                   # :93  mul, mul, add
+    return out.reshape(x.shape).astype(dtype)                   # :105
+
+
+def linearize(x, w, g0, hinv, dtype=np.float32):
+    """PCA reconstruct -> ``_increase`` -> ``apply_rf``: what the inference
+    graph does between ``Dense(11)`` and ``B_pred``
+    (linearization_net.py:325-328, test_real_refinement.py:94-95)."""
+    curve = increase(invcrf_pca_w_2_invcrf(w, g0, hinv, dtype), dtype)
+    return apply_rf(x, curve, dtype), curve

@@ -1,0 +1,78 @@
+"""BASELINE.json's full-size configurations on the GPU, checked through size-independent
+properties (the oracle is too slow there) plus oracle parity on a sampled image."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(shape, seed=0):
+    return np.random.default_rng(seed).random(shape, dtype=np.float32)
+
+
+def test_config2_pooled_hist_full(shdr_gpu):
+    """32 x 512 x 512: partition of unity survives the pool; one image checked against the oracle."""
+    img = rnd((32, 512, 512, 3), 1)
+    img = 0.0625 + img * 0.875            # keep every value inside [1/2B, 1-1/2B] for B=4,8,16... B=4: [.125,.875]
+    img = 0.125 + (img - 0.0625) / 0.875 * 0.75
+    out = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    assert out.shape == (32, 512, 512, 84) and out.min() >= 0 and out.max() <= 1
+    for off, B in ((0, 4), (12, 8), (36, 16)):
+        s = out[..., off:off + 3 * B].reshape(32, 512, 512, B, 3).sum(3)
+        assert np.abs(s - 1).max() < 2e-6          # sum over bins of the pooled votes == 1
+    ref = oracle.hist_multi(img[7:8], pool_k=16)
+    assert np.all(np.abs(out[7:8] - ref) <= 1e-5 * np.abs(ref))
+
+
+def test_config3_apply_full(shdr_gpu, emor):
+    """16 x 1024 x 1024: identity curve returns x, monotone curve keeps order, sampled oracle parity."""
+    _, g0, hinv = emor
+    x = rnd((16, 1024, 1024, 3), 2)
+    w = np.random.default_rng(3).normal(0, 0.5, (16, 11)).astype(np.float32)
+    dx = shdr_gpu.DeviceArray.from_numpy(x)
+    ident = np.tile(np.linspace(0, 1, 1024, dtype=np.float32), (16, 1))
+    y = shdr_gpu.apply_rf(dx, shdr_gpu.DeviceArray.from_numpy(ident)).numpy()
+    assert np.abs(y - x).max() <= 2.4e-7
+    y, curve = shdr_gpu.linearize(dx, shdr_gpu.DeviceArray.from_numpy(w))
+    y, curve = y.numpy(), curve.numpy()
+    rc = oracle.increase(oracle.invcrf_pca_w_2_invcrf(w, g0, hinv))
+    assert np.abs(curve - rc).max() <= 5e-6
+    for b in (0, 15):
+        order = np.argsort(x[b].ravel(), kind="stable")
+        assert np.all(np.diff(y[b].ravel()[order]) >= -1e-7)      # monotone curve -> order preserved
+    assert np.abs(y[5] - oracle.apply_rf(x[5:6], rc[5:6])[0]).max() <= 1e-5
+    assert np.array_equal(y[5], oracle.apply_rf(x[5:6], curve[5:6])[0])   # bit-exact given the same curve
+
+
+def test_config4_frontend_full(shdr_gpu):
+    """8 x 512 x 512 front end: slices equal the stand-alone layers; one image vs the oracle."""
+    img = rnd((8, 512, 512, 3), 4)
+    d = shdr_gpu.DeviceArray.from_numpy(img)
+    f = shdr_gpu.frontend(d).numpy()
+    assert np.array_equal(f[..., :3], img)
+    assert np.array_equal(f[..., 3:9], shdr_gpu.sobel_edges6(d).numpy())
+    assert np.array_equal(f[..., 9:21], shdr_gpu.histogram_layer(d, 4).numpy())
+    assert np.array_equal(f[..., 21:45], shdr_gpu.histogram_layer(d, 8).numpy())
+    assert np.array_equal(f[..., 45:], shdr_gpu.histogram_layer(d, 16).numpy())
+    assert np.array_equal(f[3], oracle.frontend(img[3:4])[0])
+
+
+def test_config5_4k_frame(shdr_gpu, emor):
+    """One 3840x2160 frame: front end + linearize; row-tile sharding gives the same bytes."""
+    _, g0, hinv = emor
+    img = rnd((1, 2160, 3840, 3), 5)
+    d = shdr_gpu.DeviceArray.from_numpy(img)
+    f = shdr_gpu.frontend(d).numpy()
+    rows = slice(1000, 1016)
+    ref = oracle.frontend(img[:, 999:1017])[:, 1:-1]          # interior rows: halo rows are real data
+    assert np.array_equal(f[:, rows], ref)
+    # tile sharding: 4 row tiles with a 1-row read-only halo reproduce the frame
+    for (y0, y1, i0, i1) in shdr_gpu.row_tiles(2160, 4, 1, 1)[1:3]:
+        part = shdr_gpu.frontend(shdr_gpu.DeviceArray.from_numpy(img[:, i0:i1])).numpy()
+        assert np.array_equal(part[:, y0 - i0:y1 - i0, :, 9:], f[:, y0:y1, :, 9:])
+        assert np.array_equal(part[:, y0 - i0:y1 - i0, :, :9], f[:, y0:y1, :, :9])
+    w = np.random.default_rng(99).normal(0, 0.5, (1, 11)).astype(np.float32)
+    y, curve = shdr_gpu.linearize(d, shdr_gpu.DeviceArray.from_numpy(w))
+    assert np.array_equal(y.numpy()[:, :64], oracle.apply_rf(img[:, :64], curve.numpy()))
