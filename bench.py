@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Linearization-Net per-pixel path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # native sm_100a kernels
+    python bench.py --impl reference --gpus N --steps K ...  # the reference path on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input.  The default workload
+is BASELINE.json configs[1]: soft histogram B={4,8,16} fused with the 16x16 'same' average pool,
+batch 32 at 512x512x3 fp32 per GPU (weak scaling: every rank owns its own batch, no collective).
+`value` is whole-job Mpixel/s with inputs resident in HBM; `e2e` is the same metric through the
+host-buffer API (pinned host memory, H2D and D2H copies inside the timed region).
+
+PyTorch is used here for plumbing only (process group, device selection, CUDA events on the
+stream the kernels are launched on); every timed kernel is launched by libshdr through ctypes.
+The oracle is imported only for the CPU baseline / --impl reference legs.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (batch per GPU, h, w, algorithmic bytes per pixel, description)
+    "config2": (32, 512, 512, 348,
+                "configs[1]: soft histogram B={4,8,16} + 16x16/1/'same' avg-pool fused, batch 32 x 512x512x3 fp32 -> [32,512,512,84]"),
+    "config3": (16, 1024, 1024, 24,
+                "configs[2]: inverse-CRF apply (EMoR PCA build + _increase + per-pixel lerp lookup), batch 16 x 1024x1024x3"),
+    "config4": (8, 512, 512, 384,
+                "configs[3] kernels only: 93-channel front end (Sobel + hist 4/8/16 + concat), batch 8 x 512x512x3"),
+    "config5": (8, 2160, 3840, 408,
+                "configs[4]: 3840x2160 frames, front end (93 ch) + inverse-CRF linearize, 8 frames per GPU"),
+    "config2u": (32, 512, 512, 348,
+                 "soft histogram B={4,8,16} WITHOUT the pool (as the reference ships it), batch 32 x 512x512x3 -> 84 ch"),
+}
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic(workload):
+    """dram__bytes_read+write per launch of the dominant kernel from the committed ncu capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def emor_table():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "invemor_f32.npz"))
+    return z["g0"], z["hinv"]
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, f"/tmp/shdr_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_fn(workload, n_items):
+    """Returns (fn, pixels): fn() runs the oracle (NumPy restatement of the TF2 path, one full-tensor
+    op per TF op) on n_items images of the workload with one host thread per image."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    _, h, w, _, _ = WORKLOADS[workload]
+    g0, hinv = emor_table()
+    rng = np.random.default_rng(1)
+    imgs = [rng.random((1, h, w, 3), dtype=np.float32) for _ in range(n_items)]
+    ws = [rng.normal(0, 0.5, (1, 11)).astype(np.float32) for _ in range(n_items)]
+
+    def one(i):
+        if workload == "config2":
+            oracle.hist_multi(imgs[i], pool_k=16)
+        elif workload == "config2u":
+            oracle.hist_multi(imgs[i])
+        elif workload == "config3":
+            oracle.linearize(imgs[i], ws[i], g0, hinv)
+        elif workload == "config4":
+            oracle.frontend(imgs[i])
+        else:
+            oracle.frontend(imgs[i])
+            oracle.linearize(imgs[i], ws[i], g0, hinv)
+
+    pool = ThreadPoolExecutor(n_items)
+
+    def fn():
+        list(pool.map(one, range(n_items)))
+    return fn, n_items * h * w
+
+
+def cpu_threads():
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = cpu_threads()
+    wl = args.workload
+    per_thread = 1
+    fn, px = cpu_step_fn(wl, cores * per_thread)
+    for _ in range(args.warmup):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = px / dt / 1e6
+    sample = (f"{cores} images {WORKLOADS[wl][1]}x{WORKLOADS[wl][2]}x3 per step (one per host thread) of the same "
+              f"synthetic distribution; NumPy restatement of the TF2 path (TensorFlow is not installable here), not TF")
+    line = {
+        "impl": "reference", "metric": "Mpixel/s", "value": val, "unit": "Mpixel/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[wl][4], "name": wl},
+        "cpu_baseline": {"value": val, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ native arm
+def run_native(args):
+    import torch
+    import shdr
+    from shdr import _native as N
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    shdr.require_gpu()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    g0, hinv = emor_table()
+    shdr.set_emor_table(g0, hinv)
+
+    wl = args.workload
+    nb, h, w, bpp, desc = WORKLOADS[wl]
+    px = nb * h * w
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1 + rank)
+    img = torch.rand((nb, h, w, 3), device=dev, dtype=torch.float32, generator=gen)
+    wts = (torch.randn((nb, 11), device=dev, generator=gen) * 0.5).contiguous()
+    out_ch = {"config2": 84, "config2u": 84, "config3": 3, "config4": 93, "config5": 93}[wl]
+    out = torch.empty((nb, h, w, out_ch), device=dev, dtype=torch.float32)
+    lin = torch.empty((nb, h, w, 3), device=dev) if wl in ("config3", "config5") else None
+    curve = torch.empty((nb, 1024), device=dev)
+    stream = torch.cuda.current_stream()
+    sh = stream.cuda_stream
+    ip, op_, wp, cp = img.data_ptr(), out.data_ptr(), wts.data_ptr(), curve.data_ptr()
+
+    def step():
+        if wl == "config2":
+            N.check(N.lib.shdr_hist_multi_f32(ip, op_, nb, h, w, 16, sh))
+        elif wl == "config2u":
+            N.check(N.lib.shdr_hist_multi_f32(ip, op_, nb, h, w, 0, sh))
+        elif wl == "config3":
+            N.check(N.lib.shdr_linearize_f32(ip, wp, op_, cp, nb, h * w * 3, sh))
+        elif wl == "config4":
+            N.check(N.lib.shdr_frontend_f32(ip, op_, nb, h, w, 0, sh))
+        else:
+            N.check(N.lib.shdr_frontend_f32(ip, op_, nb, h, w, 0, sh))
+            N.check(N.lib.shdr_linearize_f32(ip, wp, lin.data_ptr(), cp, nb, h * w * 3, sh))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # L2 policy: per-step working set (>= 400 MB) exceeds the 126 MB L2, so no flush is needed
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = shdr.launch_count()
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    launches = shdr.launch_count() - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_step = total_ms / args.steps
+    value = world * px / (ms_step * 1e-3) / 1e6
+    kern_ms = statistics.mean(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+
+    # ---- e2e: host buffers through the public host API, copies inside the timed region
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    src = shdr.PinnedArray((nb, h, w, 3))
+    src.array[...] = np.random.default_rng(7 + rank).random((nb, h, w, 3), dtype=np.float32)
+    in_b, out_b = h * w * 3 * 4, h * w * out_ch * 4
+    if wl in ("config3",):
+        dst = shdr.PinnedArray((nb, h, w, 3))
+        wh = np.random.default_rng(3).normal(0, 0.5, (nb, 11)).astype(np.float32)
+
+        def e2e_step():
+            shdr.linearize_host(src.array, wh, out=dst.array, device=local)
+        h2d, d2h = nb * in_b + wh.nbytes, nb * in_b + nb * 4096
+    else:
+        dst = shdr.PinnedArray((nb, h, w, out_ch))
+        pk = 16 if wl == "config2" else 0
+        fn = N.lib.shdr_hist_multi_f32 if wl in ("config2", "config2u") else N.lib.shdr_frontend_f32
+
+        def op(d_in, d_out, m, st, _i0):
+            N.check(fn(d_in, d_out, m, h, w, pk, st))
+        chunk = max(1, min(nb, (256 << 20) // out_b))
+        pipe = shdr.HostPipeline(op, in_b, out_b, chunk, device=local, slots=3)
+
+        def e2e_step():
+            pipe.run(src.array, dst.array, nb)
+        h2d, d2h = nb * in_b, nb * out_b
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * px / (float(t.item()) * 1e-3) / 1e6
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = load_peak()
+        achieved = px * bpp / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "name": wl, "batch_per_gpu": nb, "h": h, "w": w,
+                       "l2": f"per-step working set {px * bpp / 1e6:.0f} MB > 126 MB L2, no flush needed",
+                       "parallelism": f"batch-sharded x{world}, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": load_traffic(wl), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": px * bpp, "kernel_ms": kern_ms},
+            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": float(t.item())},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = cpu_threads()
+            fn_cpu, cpx = cpu_step_fn(wl, cores)
+            fn_cpu() if args.cpu_warm else None
+            t0 = time.perf_counter()
+            fn_cpu()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": cpx / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                "sample": f"{cores} images {h}x{w}x3 (one per host thread), one pass, {dt:.1f} s; NumPy "
+                          f"restatement of the TF2 path (TensorFlow not installable here)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-warm", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

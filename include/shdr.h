@@ -91,7 +91,7 @@ int shdr_frontend_f32(const float* img, float* out, int n, int h, int w,
  * monotone != 0 additionally applies model._increase (:368-392). */
 int shdr_invcrf_build_f32(const float* w, float* curve, int b, int monotone, void* stream);
 
-/* model._increase(rf) (:368-392) on rf[b,k], 2 <= k <= 65536. */
+/* model._increase(rf) (:368-392) on rf[b,k], 2 <= k <= 49152 (the curve lives in shared memory). */
 int shdr_increase_f32(const float* rf, float* out, int b, int k, void* stream);
 
 /* tf_utils.apply_rf(x, rf) (tf_utils.py:95-105): x[b, elems_per_item], rf[b,k]. */

@@ -22,6 +22,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int cuda_fail(cudaError_t e, const char* what) {
+  cudaGetLastError();   // clear the (non-sticky) error so that it is not reported again by a later call
   set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return SHDR_ERR_CUDA;
 }

@@ -266,7 +266,7 @@ extern "C" int shdr_invcrf_build_f32(const float* w, float* curve, int b, int mo
 
 extern "C" int shdr_increase_f32(const float* rf, float* out, int b, int k, void* stream) {
   SHDR_REQUIRE(rf && out, "increase: NULL pointer");
-  SHDR_REQUIRE(b >= 0 && k >= 2 && k <= 65536, "increase: b=%d k=%d (need b>=0, 2<=k<=65536)", b, k);
+  SHDR_REQUIRE(b >= 0 && k >= 2 && k <= 49152, "increase: b=%d k=%d (need b>=0, 2<=k<=49152)", b, k);
   if (b == 0) return SHDR_OK;
   DeviceGuard g(out);
   if (g.status != SHDR_OK) return g.status;

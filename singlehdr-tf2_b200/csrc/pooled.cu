@@ -6,34 +6,43 @@
 //   TF SAME semantics: window rows [y-7, y+8], cols [x-7, x+8] clipped to the image, average over
 //   the in-bounds elements only (81 at the top-left corner, 64 at bottom-right, 256 inside).
 //
-// Design: the 3B-channel un-pooled histogram NEVER goes to HBM.  A CTA owns a 16x64 output tile,
-// stages the (16+15)x(64+15)x3 input tile in shared memory once, and for every group of 12 output
-// channels (4 bins x RGB) evaluates the votes on the fly and box-filters them separably:
-//   pass 1 (vertical)   one thread per (column, channel): 31 votes in registers -> 16 window sums
-//   pass 2 (horizontal) one thread per (row, 16-column block, channel): 31 column sums -> 16 outputs
+// Design: the 3B-channel un-pooled histogram NEVER goes to HBM.  A CTA owns a 32x64 output tile,
+// stages the (32+15)x(64+15)x3 input tile in shared memory once (transposed: one contiguous
+// 47-row column per (channel, x), so a thread fetches its column with 12 LDS.128), and for every
+// group of 12 output channels (4 bins x RGB) evaluates the votes on the fly and box-filters them
+// separably:
+//   pass 1 (vertical)   one thread per (column, channel): 47 votes in registers -> 32 window sums
+//   pass 2 (horizontal) one thread per (row, 16-column block, channel): 31 column sums (8 LDS.128)
+//                       -> 16 outputs, scaled by 1/count, stored with the group's 12 channels of a
+//                       pixel in adjacent lanes
 // Window sums use the van Herk / Gil-Werman split (suffix sums of one 16-block + prefix sums of the
 // next): ~2.8 adds per output, only ADDITIONS of non-negative votes -- no running-sum subtraction,
 // so no cancellation and an exactly-zero window stays exactly zero (the 1e-5 RELATIVE gate).
 // Out-of-image taps hold a sentinel whose vote is 0 for every bin, so the border needs no branches
-// in the sums; the divide uses the true in-bounds count.
+// in the sums; border tiles divide by the true in-bounds count, interior tiles multiply by the exact
+// 1/256.
 //
 // Roofline: 12 B/px read + 12*B B/px written (348 B/px for B = 4, 8, 16) -> HBM-bound by intent;
-// the instruction/shared-memory budget per pixel is what the kernel has to fit under.
+// the instruction budget per pixel (~13.5 issue clocks per pixel per SM at the roofline) is what the
+// kernel has to fit under, which is why every inner loop is register-resident and vectorised.
 #include "common.cuh"
 
 namespace shdr {
 
 constexpr int PK = 16;                 // pool window
 constexpr int PB = (PK - 1) / 2;       // 7 taps before   [TF-sem] SAME: (k-1)//2 before, rest after
-constexpr int PT_H = 16, PT_W = 64;    // output tile
-constexpr int IN_H = PT_H + PK - 1;    // 31
+constexpr int PA = PK - 1 - PB;        // 8 taps after
+constexpr int PT_H = 32, PT_W = 64;    // output tile
+constexpr int IN_H = PT_H + PK - 1;    // 47
 constexpr int IN_W = PT_W + PK - 1;    // 79
+constexpr int IPITCH = 52;             // floats per transposed input column (47 + pad); 13 x 16 B -> LDS.128, odd chunk stride
+constexpr int VPITCH = 84;             // floats per (row, channel) line of column sums (79 + pad); 21 x 16 B
 constexpr int CG = 12;                 // channels per group: 4 bins x RGB
-constexpr int VPX = 13;                // odd per-pixel stride of the column-sum buffer
-constexpr int VROW = 1036;             // >= IN_W*VPX (1027) and == 12 (mod 32): pass-2 lanes hit 32 banks
-constexpr int POOL_THREADS = 256;
+constexpr int POOL_THREADS = 512;
 constexpr int MAX_GROUPS = 16;
 constexpr float SENTINEL = -8.0f;      // |(-8) - centre| >= 8 > 1/B  ->  vote 0 for every bin
+constexpr int SI_FLOATS = 3 * IN_W * IPITCH;       // 12324
+constexpr int SV_FLOATS = PT_H * CG * VPITCH;      // 32256
 
 struct PoolGroup {
   float nbins;     // float(B)
@@ -47,42 +56,47 @@ struct PoolParams {
   int ngroups;
 };
 
-// window sums of 16 over 31 values held in registers, in place:
-//   a[0..15]  <- suffix sums of block A,  a[16..30] <- prefix sums of block B
-//   result r  =  a[0] (r = 0)  |  a[r] + a[15 + r] (r = 1..15)
-__device__ __forceinline__ void vanherk31(float (&a)[IN_H]) {
-#pragma unroll
-  for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);
-#pragma unroll
-  for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);
+template <bool POW2>
+__device__ __forceinline__ float vote(float v, float centre, float thr, float nbins) {
+  return POW2 ? hist_vote_pow2(v, centre, nbins) : hist_vote(v, centre, thr, nbins);
 }
 
-__global__ void __launch_bounds__(POOL_THREADS)
+template <bool POW2>
+__global__ void __launch_bounds__(POOL_THREADS, 1)
 k_hist_pooled(const float* __restrict__ img, float* __restrict__ out, int h, int w, int ostride,
               const __grid_constant__ PoolParams prm) {
-  extern __shared__ float smem[];
-  float* sI = smem;                        // [IN_H][IN_W][3]
-  float* sV = smem + IN_H * IN_W * 3;      // [PT_H][VROW]   (pixel stride VPX, channel fastest)
+  extern __shared__ __align__(16) float smem[];
+  float* sI = smem;                 // [3][IN_W][IPITCH]  transposed input tile (+halo)
+  float* sV = smem + SI_FLOATS;     // [PT_H][CG][VPITCH] column sums of the current channel group
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
   const long long n = blockIdx.z;
   const float* im = img + n * h * w * 3;
 
-  // stage the input tile with halo; out-of-image taps get the sentinel
+  // ---- stage the input tile: coalesced global reads, transposed shared writes; sentinel outside
   for (int i = tid; i < IN_H * IN_W * 3; i += POOL_THREADS) {
     const int r = i / (IN_W * 3);
     const int rem = i - r * (IN_W * 3);
+    const int xc = rem / 3;
+    const int c = rem - xc * 3;
     const int gy = y0 - PB + r;
-    const int gx = x0 - PB + rem / 3;
+    const int gx = x0 - PB + xc;
     float v = SENTINEL;
     if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = __ldg(im + ((long long)gy * w + (x0 - PB)) * 3 + rem);
-    sI[i] = v;
+    sI[(c * IN_W + xc) * IPITCH + r] = v;
+  }
+  for (int i = tid; i < 3 * IN_W * (IPITCH - IN_H); i += POOL_THREADS) {   // pad rows 47..51
+    const int col = i / (IPITCH - IN_H);
+    sI[col * IPITCH + IN_H + (i - col * (IPITCH - IN_H))] = SENTINEL;
   }
   __syncthreads();
 
+  // every window of this tile is complete and in bounds?
+  const bool interior = (y0 >= PB) && (y0 + PT_H + PA <= h) && (x0 >= PB) && (x0 + PT_W + PA <= w);
+
   for (int gi = 0; gi < prm.ngroups; ++gi) {
     const PoolGroup g = prm.g[gi];
-    // ---- pass 1: vertical window sums, one (column, channel) per thread
+    // ---- pass 1: vertical 16-window sums; item = (channel-in-group, column)
     const int items1 = IN_W * g.nch;
     for (int it = tid; it < items1; it += POOL_THREADS) {
       const int cb = it / IN_W;            // channel within group = bin*3 + c
@@ -90,40 +104,74 @@ k_hist_pooled(const float* __restrict__ img, float* __restrict__ out, int h, int
       const int bin = cb / 3;
       const int c = cb - bin * 3;
       const float centre = __fdiv_rn((float)(2 * (g.bin0 + bin) + 1), 2.0f * g.nbins);
-      float a[IN_H];
+      const float4* col = reinterpret_cast<const float4*>(sI + (c * IN_W + xc) * IPITCH);
+      float a[48];
 #pragma unroll
-      for (int r = 0; r < IN_H; ++r) a[r] = hist_vote(sI[(r * IN_W + xc) * 3 + c], centre, g.thr, g.nbins);
-      vanherk31(a);
-      float* vcol = sV + xc * VPX + cb;
+      for (int q = 0; q < 12; ++q) {
+        const float4 t = col[q];
+        a[4 * q + 0] = vote<POW2>(t.x, centre, g.thr, g.nbins);
+        a[4 * q + 1] = vote<POW2>(t.y, centre, g.thr, g.nbins);
+        a[4 * q + 2] = vote<POW2>(t.z, centre, g.thr, g.nbins);
+        a[4 * q + 3] = vote<POW2>(t.w, centre, g.thr, g.nbins);
+      }
+      // blocks A = a[0..15], B = a[16..31], C = a[32..46]; output row r sums input rows r..r+15
+      float bs[16];                        // suffix sums of B
+      bs[15] = a[31];
+#pragma unroll
+      for (int i = 14; i >= 0; --i) bs[i] = __fadd_rn(a[16 + i], bs[i + 1]);
+#pragma unroll
+      for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);            // suffix of A
+#pragma unroll
+      for (int i = 17; i < 32; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);            // prefix of B
+#pragma unroll
+      for (int i = 33; i < 47; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);            // prefix of C
+      float* vcol = sV + cb * VPITCH + xc;
       vcol[0] = a[0];
 #pragma unroll
-      for (int r = 1; r < PT_H; ++r) vcol[r * VROW] = __fadd_rn(a[r], a[15 + r]);
+      for (int r = 1; r < 16; ++r) vcol[r * (CG * VPITCH)] = __fadd_rn(a[r], a[15 + r]);
+      vcol[16 * (CG * VPITCH)] = bs[0];
+#pragma unroll
+      for (int r = 17; r < 32; ++r) vcol[r * (CG * VPITCH)] = __fadd_rn(bs[r - 16], a[15 + r]);
     }
     __syncthreads();
-    // ---- pass 2: horizontal window sums, divide by the in-bounds count, store
-    const int items2 = g.nch * PT_H * (PT_W / 16);
+
+    // ---- pass 2: horizontal 16-window sums, scale, store; item = (16-col block, row, channel)
+    const int lines = PT_H * g.nch;        // (row, channel) lines, channel fastest
+    const int items2 = lines * (PT_W / 16);
     for (int it = tid; it < items2; it += POOL_THREADS) {
-      const int ch = it % g.nch;
-      const int t = it / g.nch;
-      const int r = t % PT_H;
-      const int xb = t / PT_H;
+      const int xb = it / lines;
+      const int line = it - xb * lines;
+      const int r = line / g.nch;
+      const int ch = line - r * g.nch;
       const int gy = y0 + r;
       const int gx0 = x0 + xb * 16;
-      if (gy >= h || gx0 >= w) continue;
-      const float* vrow = sV + r * VROW + xb * 16 * VPX + ch;
-      float a[IN_H];
+      if (!interior && (gy >= h || gx0 >= w)) continue;
+      const float4* vl = reinterpret_cast<const float4*>(sV + (r * CG + ch) * VPITCH + xb * 16);
+      float a[32];
 #pragma unroll
-      for (int j = 0; j < IN_H; ++j) a[j] = vrow[j * VPX];
-      vanherk31(a);
-      const int cy = min(gy + (PK - 1 - PB), h - 1) - max(gy - PB, 0) + 1;
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = vl[q];
+        a[4 * q + 0] = t.x; a[4 * q + 1] = t.y; a[4 * q + 2] = t.z; a[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);            // suffix of cols 0..15
+#pragma unroll
+      for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);            // prefix of cols 16..30
       float* o = out + ((n * h + gy) * w + gx0) * ostride + g.out_off + ch;
+      if (interior) {
+        o[0] = a[0] * (1.0f / 256.0f);     // exact: power-of-two count
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int gx = gx0 + j;
-        if (gx < w) {
-          const int cx = min(gx + (PK - 1 - PB), w - 1) - max(gx - PB, 0) + 1;
-          const float sum = (j == 0) ? a[0] : __fadd_rn(a[j], a[15 + j]);
-          o[(long long)j * ostride] = __fdiv_rn(sum, (float)(cy * cx));
+        for (int j = 1; j < 16; ++j) o[(long long)j * ostride] = __fadd_rn(a[j], a[15 + j]) * (1.0f / 256.0f);
+      } else {
+        const int cy = min(gy + PA, h - 1) - max(gy - PB, 0) + 1;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int gx = gx0 + j;
+          if (gx < w) {
+            const int cx = min(gx + PA, w - 1) - max(gx - PB, 0) + 1;
+            const float sum = (j == 0) ? a[0] : __fadd_rn(a[j], a[15 + j]);
+            o[(long long)j * ostride] = __fdiv_rn(sum, (float)(cy * cx));
+          }
         }
       }
     }
@@ -131,22 +179,32 @@ k_hist_pooled(const float* __restrict__ img, float* __restrict__ out, int h, int
   }
 }
 
+template <bool POW2>
+static int launch_pooled_t(const float* img, float* out, int h, int w, int ostride, dim3 grid,
+                           const PoolParams& prm, cudaStream_t st) {
+  const size_t smem = (size_t)(SI_FLOATS + SV_FLOATS) * sizeof(float);
+  SHDR_CUDA(cudaFuncSetAttribute(k_hist_pooled<POW2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_hist_pooled<POW2><<<grid, POOL_THREADS, smem, st>>>(img, out, h, w, ostride, prm);
+  SHDR_LAUNCH_CHECK("k_hist_pooled");
+  return SHDR_OK;
+}
+
 int launch_hist_pooled(const float* img, float* out, int n, int h, int w, const int* bins, int nbins,
                        int ostride, int ooff, cudaStream_t st) {
-  static const size_t smem = (size_t)(IN_H * IN_W * 3 + PT_H * VROW) * sizeof(float);
-  SHDR_CUDA(cudaFuncSetAttribute(k_hist_pooled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((w + PT_W - 1) / PT_W, (h + PT_H - 1) / PT_H, n);
   SHDR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "hist_pooled: grid (%u,%u,%u) out of range", grid.x, grid.y, grid.z);
 
   PoolParams prm;
   prm.ngroups = 0;
+  bool pow2 = true;
   int off = ooff;
   auto flush = [&]() -> int {
     if (prm.ngroups == 0) return SHDR_OK;
-    k_hist_pooled<<<grid, POOL_THREADS, smem, st>>>(img, out, h, w, ostride, prm);
-    SHDR_LAUNCH_CHECK("k_hist_pooled");
+    int rc = pow2 ? launch_pooled_t<true>(img, out, h, w, ostride, grid, prm, st)
+                  : launch_pooled_t<false>(img, out, h, w, ostride, grid, prm, st);
     prm.ngroups = 0;
-    return SHDR_OK;
+    pow2 = true;
+    return rc;
   };
   for (int i = 0; i < nbins; ++i) {
     const int B = bins[i];
@@ -157,6 +215,7 @@ int launch_hist_pooled(const float* img, float* out, int n, int h, int w, const 
       g.bin0 = b0;
       g.nch = 3 * (B - b0 < CG / 3 ? B - b0 : CG / 3);
       g.out_off = off + 3 * b0;
+      pow2 = pow2 && ((B & (B - 1)) == 0);
       if (prm.ngroups == MAX_GROUPS) {
         int rc = flush();
         if (rc != SHDR_OK) return rc;

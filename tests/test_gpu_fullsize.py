@@ -15,8 +15,7 @@ def rnd(shape, seed=0):
 def test_config2_pooled_hist_full(shdr_gpu):
     """32 x 512 x 512: partition of unity survives the pool; one image checked against the oracle."""
     img = rnd((32, 512, 512, 3), 1)
-    img = 0.0625 + img * 0.875            # keep every value inside [1/2B, 1-1/2B] for B=4,8,16... B=4: [.125,.875]
-    img = 0.125 + (img - 0.0625) / 0.875 * 0.75
+    img = np.float32(0.125) + img * np.float32(0.75)    # inside [1/2B, 1-1/2B] for B = 4, 8, 16
     out = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
     assert out.shape == (32, 512, 512, 84) and out.min() >= 0 and out.max() <= 1
     for off, B in ((0, 4), (12, 8), (36, 16)):
@@ -41,7 +40,7 @@ def test_config3_apply_full(shdr_gpu, emor):
     assert np.abs(curve - rc).max() <= 5e-6
     for b in (0, 15):
         order = np.argsort(x[b].ravel(), kind="stable")
-        assert np.all(np.diff(y[b].ravel()[order]) >= -1e-7)      # monotone curve -> order preserved
+        assert np.all(np.diff(y[b].ravel()[order]) >= -6e-7)      # monotone curve -> order preserved (up to the 3 roundings of the lerp)
     assert np.abs(y[5] - oracle.apply_rf(x[5:6], rc[5:6])[0]).max() <= 1e-5
     assert np.array_equal(y[5], oracle.apply_rf(x[5:6], curve[5:6])[0])   # bit-exact given the same curve
 

@@ -169,13 +169,23 @@ def test_w_zero_is_g0(shdr_gpu, emor):
     assert np.array_equal(c, np.stack([g0] * 3))
 
 
-@pytest.mark.parametrize("k", [2, 3, 64, 1000, 1024, 1025, 4099, 65536])
+@pytest.mark.parametrize("k", [2, 3, 64, 1000, 1024, 1025, 4099, 49152])
 def test_increase_generic_k(shdr_gpu, k):
     rf = np.cumsum(np.random.default_rng(k).normal(0.2, 1.0, (3, k)), axis=1).astype(np.float32)
+    if k == 2:
+        rf[0] = [0.25, 0.75]          # rising: -> [0, 1]
+        rf[1] = [0.75, 0.25]          # falling: g + relu(-g) = 0 -> 0/0 = NaN, like the reference
     got = shdr_gpu._increase(shdr_gpu.DeviceArray.from_numpy(rf)).numpy()
     ref = oracle.increase(rf.astype(np.float64), np.float64)
-    assert np.abs(got - ref).max() <= ATOL_CURVE * max(1, k // 4096)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(got[ok] - ref[ok]).max() <= ATOL_CURVE * max(1, k // 4096)
     assert (got[:, 0] == 0).all()
+
+
+def test_increase_k_limit(shdr_gpu):
+    with pytest.raises(shdr_gpu.ShdrError, match="49152"):
+        shdr_gpu._increase(shdr_gpu.DeviceArray.from_numpy(np.zeros((1, 49153), np.float32)))
 
 
 def test_increase_constant_curve_nan_like_reference(shdr_gpu):
