@@ -1,0 +1,400 @@
+// pooled_ws.cu -- warp-specialised, persistent kernel for the fused soft histogram + 16x16 'same'
+// average pool, fast path (power-of-two B, dense [n,h,w,C] output, even image width).  See pooled.cu
+// for the reference behaviour restated, the numerics and the generic block-synchronous kernel.
+//
+// Two measured facts shape this kernel (profiles/r1, tools/microbench/store_patterns.cu):
+//  1. B200 absorbs PARTIAL 32-byte sectors ~5x slower than full ones: writing the 84-channel output
+//     as 48-byte (12-channel) fragments caps at 1.6 TB/s no matter how little compute runs, while
+//     scattered but whole, aligned sectors reach 4.5 TB/s.  A pixel is 336 B = 10.5 sectors, so
+//     sector boundaries fall on channel multiples of 8 for even pixels and on 8k+4 for odd pixels.
+//     => the channel axis is processed in UNITS OF 8 CHANNELS (one sector); an even pixel stores its
+//     8 fresh channels directly; an odd pixel stores {4 channels held from the previous unit in
+//     registers, 4 fresh channels} with ONE instruction (8 adjacent lanes = one whole sector).  The
+//     sector that straddles an (even, odd) pixel pair is written at the last unit from the even
+//     pixel's 4 fresh channels and the odd pixel's first 4 channels held since unit 0.
+//  2. A block-synchronous two-pass kernel idles at barriers because the passes have different item
+//     counts.  => ONE persistent CTA per SM runs a producer/consumer pipeline over (tile, unit):
+//       producers (10 warps)  votes + vertical 16-window sums  -> column-sum ring sV[3 stages]
+//       consumers ( 8 warps)  horizontal 16-window sums, scale, whole-sector stores  <- sV[stage]
+//     with mbarrier hand-off and no block-wide barrier; the next tile's input (+halo) is prefetched
+//     with cp.async into the other half of a double-buffered, transposed input tile.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace shdr {
+
+namespace ws {
+constexpr int PK = 16, PB = 7, PA = 8;
+constexpr int PT_H = 16, PT_W = 64;
+constexpr int IN_H = PT_H + PK - 1;    // 31
+constexpr int IN_W = PT_W + PK - 1;    // 79
+constexpr int IPITCH = 36;             // floats per transposed input column (31 rows + pad): 9 x 16 B
+constexpr int VPITCH = 84;             // floats per (row, channel) line of column sums (79 + pad): 21 x 16 B
+constexpr int UC = 8;                  // channels per unit = one 32-byte sector
+constexpr int NSTAGE = 3;
+constexpr int NPROD = 320, NCONS = 256, THREADS = NPROD + NCONS;
+constexpr int SI_FLOATS = 3 * IN_W * IPITCH;     // 8532
+constexpr int SV_FLOATS = PT_H * UC * VPITCH;    // 10752
+constexpr int RC_FLOATS = PT_W + PT_H;           // 80
+constexpr int MAXC = 192;                        // up to 64 bins x RGB per launch
+constexpr float SENTINEL = -8.0f;
+constexpr int HEAD_FLOATS = PT_H * (PT_W / 2) * 4;   // odd pixels' channels 0..3, parked from unit 0 to the last unit
+constexpr size_t SMEM_BYTES =
+    (size_t)(2 * SI_FLOATS + NSTAGE * SV_FLOATS + 2 * RC_FLOATS + 3 * MAXC + HEAD_FLOATS) * 4 + 2 * NSTAGE * 8;
+
+struct Params {
+  float centre[MAXC];        // bin centre of every output channel, fp32 (2i-1)/(2B)
+  float nbins[MAXC];         // float(B) of the channel's histogram
+  unsigned char col[MAXC];   // colour plane (0..2) the channel reads
+  int C;                     // output channels per pixel (multiple of 4)
+  int n, h, w;
+  int tiles_x, tiles_y, tiles_total;
+  int dbg;                   // profiling experiments only (SHDR_POOL_DBG): 0 = normal, 1 = no global stores
+};
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct TileCoord { int n, y0, x0; };
+__device__ __forceinline__ TileCoord tile_coord(int t, const Params& p) {
+  TileCoord c;
+  const int per_img = p.tiles_x * p.tiles_y;
+  c.n = t / per_img;
+  const int r = t - c.n * per_img;
+  const int ty = r / p.tiles_x;
+  c.y0 = ty * PT_H;
+  c.x0 = (r - ty * p.tiles_x) * PT_W;
+  return c;
+}
+
+// producers: one thread per staged (column, colour) pair copies that column's 31 rows (transposed)
+__device__ __forceinline__ void stage_tile(float* sI, const float* __restrict__ img, const TileCoord tc, int h, int w,
+                                           int ptid) {
+  if (ptid < IN_W * 3) {
+    const int xc = ptid / 3;
+    const int c = ptid - xc * 3;
+    const int gx = tc.x0 - PB + xc;
+    float* dst = sI + (c * IN_W + xc) * IPITCH;
+    const bool xok = gx >= 0 && gx < w;
+    const float* src = img + (((long long)tc.n * h + (tc.y0 - PB)) * w + gx) * 3 + c;
+#pragma unroll 4
+    for (int r = 0; r < IN_H; ++r) {
+      const int gy = tc.y0 - PB + r;
+      if (xok && gy >= 0 && gy < h) cp_async4(dst + r, src + (long long)r * w * 3);
+      else dst[r] = SENTINEL;
+    }
+  }
+}
+
+// One consumer thread, one 16-column block of one unit: horizontal 16-window sums of its (row, channel) line,
+// scale, and whole-sector stores.  INTERIOR (tile-uniform) removes every bounds test and uses the exact 1/256;
+// PHASE (unit-uniform): 0 = first unit, 1 = middle, 2 = last unit.
+//   even pixel (sector-aligned): its 8 fresh channels are one sector; at the last unit (4 channels) lanes 4..7
+//     store the odd right neighbour's first 4 channels, parked in shared memory since unit 0 by lanes 0..3;
+//   odd pixel: {4 channels held from the previous unit (lanes 4..7), 4 fresh channels (lanes 0..3)} are one sector.
+template <int CT, bool EO, bool INTERIOR, int PHASE>
+__device__ __forceinline__ void consume_block(const float* __restrict__ vline, float* __restrict__ o, float* hp,
+                                              float (&hold)[8], const float* __restrict__ sRc, int r, int xb,
+                                              int f, int u, int C, bool active, bool rowok, int wleft, int dbg) {
+  float a[32];
+  if (active) {
+    const float4* vl = reinterpret_cast<const float4*>(vline);
+#pragma unroll
+    for (int qd = 0; qd < 8; ++qd) {
+      const float4 v = vl[qd];
+      a[4 * qd + 0] = v.x; a[4 * qd + 1] = v.y; a[4 * qd + 2] = v.z; a[4 * qd + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);     // suffix sums, cols 0..15
+#pragma unroll
+    for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);     // prefix sums, cols 16..30
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) a[i] = 0.0f;
+  }
+  float res[16];
+  if (INTERIOR) {
+    res[0] = a[0] * (1.0f / 256.0f);       // exact: power-of-two count
+#pragma unroll
+    for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(a[j], a[15 + j]) * (1.0f / 256.0f);
+  } else {
+    const float rcy = sRc[PT_W + r];
+    const float4* rc4 = reinterpret_cast<const float4*>(sRc + xb * 16);
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+      const float4 v = rc4[qd];
+      const float sc[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * qd + e;
+        const float sum = (j == 0) ? a[0] : __fadd_rn(a[j], a[15 + j]);
+        res[j] = sum * (rcy * sc[e]);      // <= 2 ulp from sum / (rows * cols)
+      }
+    }
+  }
+  if (dbg == 1) {                          // experiment: no global stores (kept live by an impossible predicate)
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc += res[j];
+    if (acc < -1.0f) o[0] = acc;
+    return;
+  }
+  const bool lo = f < 4;
+  if (!EO) {
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (INTERIOR || (rowok && j < wleft)) st_stream1(o + j * C, res[j]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int jp = 0; jp < 8; ++jp) {
+    const int je = 2 * jp, jo = je + 1;
+    const bool ok = INTERIOR || (rowok && je < wleft);     // w is even: the pair is in or out together
+    float* oe = o + je * C;
+    float* oo = o + jo * C;
+    if (PHASE == 0) {
+      if (ok) st_stream1(oe, res[je]);
+      if (lo) hp[jp * 4] = res[jo];                        // park channels 0..3 of the odd pixel
+      hold[jp] = res[jo];                                  // lanes 4..7: channels 4..7 wait for the next unit
+    } else if (PHASE == 1) {
+      if (ok) {
+        st_stream1(oe, res[je]);
+        st_stream1(lo ? oo : oo - UC, lo ? res[jo] : hold[jp]);
+      }
+      hold[jp] = res[jo];
+    } else {
+      if (ok) {
+        st_stream1(lo ? oe : oe + (C - u * UC - 4), lo ? res[je] : hp[jp * 4]);
+        st_stream1(lo ? oo : oo - UC, lo ? res[jo] : hold[jp]);
+      }
+    }
+  }
+}
+
+// EO: C == 4 (mod 8) -> pixel pitch is an odd number of half-sectors, even/odd pixels alternate alignment.
+//     C == 0 (mod 8) -> every pixel is sector-aligned (EO = false).
+// CT: compile-time channel count (pixel pitch in floats) so that store offsets are immediates; 0 = runtime.
+template <int CT, bool EO>
+__global__ void __launch_bounds__(THREADS, 1)
+k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const __grid_constant__ Params prm) {
+  extern __shared__ __align__(16) float smem[];
+  float* sI0 = smem;
+  float* sV0 = smem + 2 * SI_FLOATS;
+  float* sRc0 = sV0 + NSTAGE * SV_FLOATS;
+  float* sCentre = sRc0 + 2 * RC_FLOATS;
+  float* sNb = sCentre + MAXC;
+  int* sCol = reinterpret_cast<int*>(sNb + MAXC);
+  float* sHead = reinterpret_cast<float*>(sCol + MAXC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sHead + HEAD_FLOATS);   // full[NSTAGE], empty[NSTAGE]
+  const int tid = threadIdx.x;
+  const int h = prm.h, w = prm.w;
+  const int C = CT ? CT : prm.C;
+  const int units = (C + UC - 1) / UC;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bars + s, NPROD);
+      mbar_init(bars + NSTAGE + s, NCONS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < MAXC; i += THREADS) {
+    sCentre[i] = prm.centre[i];
+    sNb[i] = prm.nbins[i];
+    sCol[i] = prm.col[i];
+  }
+  // pad rows 31..35 of both input buffers hold the sentinel for the whole kernel
+  for (int i = tid; i < 2 * 3 * IN_W * (IPITCH - IN_H); i += THREADS) {
+    const int col = i / (IPITCH - IN_H);
+    smem[col * IPITCH + IN_H + (i - col * (IPITCH - IN_H))] = SENTINEL;
+  }
+  __syncthreads();
+
+  if (tid < NPROD) {
+    // =========================== producers: staging + pass 1 ===========================
+    const int ptid = tid;
+    int t = blockIdx.x;
+    if (t < prm.tiles_total) stage_tile(sI0, img, tile_coord(t, prm), h, w, ptid);
+    unsigned q = 0;
+    for (int k = 0; t < prm.tiles_total; t += gridDim.x, ++k) {
+      float* sI = sI0 + (k & 1) * SI_FLOATS;
+      cp_async_wait_all();
+      named_bar_sync(1, NPROD);          // tile k landed; every producer is done reading the other buffer
+      const int tn = t + gridDim.x;
+      if (tn < prm.tiles_total) stage_tile(sI0 + ((k + 1) & 1) * SI_FLOATS, img, tile_coord(tn, prm), h, w, ptid);
+
+      for (int u = 0; u < units; ++u, ++q) {
+        const unsigned s = q % NSTAGE, uu = q / NSTAGE;
+        float* sV = sV0 + s * SV_FLOATS;
+        mbar_wait(bars + NSTAGE + s, (uu & 1u) ^ 1u);   // consumers released this stage (passes at once on first use)
+        const int nchu = min(UC, C - u * UC);
+        for (int it = ptid; it < IN_W * nchu; it += NPROD) {
+          const int cb = it / IN_W;
+          const int xc = it - cb * IN_W;
+          const int ch = u * UC + cb;
+          const float centre = sCentre[ch], nb = sNb[ch];
+          const float4* col = reinterpret_cast<const float4*>(sI + (sCol[ch] * IN_W + xc) * IPITCH);
+          float a[32];
+#pragma unroll
+          for (int qd = 0; qd < 8; ++qd) {
+            const float4 v = col[qd];
+            a[4 * qd + 0] = hist_vote_pow2(v.x, centre, nb);
+            a[4 * qd + 1] = hist_vote_pow2(v.y, centre, nb);
+            a[4 * qd + 2] = hist_vote_pow2(v.z, centre, nb);
+            a[4 * qd + 3] = hist_vote_pow2(v.w, centre, nb);
+          }
+#pragma unroll
+          for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);      // suffix sums, rows 0..15
+#pragma unroll
+          for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);      // prefix sums, rows 16..30
+          float* vcol = sV + cb * VPITCH + xc;
+          vcol[0] = a[0];
+#pragma unroll
+          for (int r = 1; r < 16; ++r) vcol[r * (UC * VPITCH)] = __fadd_rn(a[r], a[15 + r]);
+        }
+        mbar_arrive(bars + s);             // release: this thread's column sums are in sV[s]
+      }
+    }
+  } else {
+    // =========================== consumers: pass 2 + whole-sector stores ===========================
+    const int ctid = tid - NPROD;
+    const int f = ctid & 7;                // channel within the unit == lane within the sector
+    const int r = (ctid >> 3) & 15;        // tile row
+    const int xbh = ctid >> 7;             // which half of the tile's four 16-column blocks
+    const bool lo = f < 4;
+    unsigned q = 0;
+    int k = 0;
+    for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x, ++k) {
+      const TileCoord tc = tile_coord(t, prm);
+      const int x0 = tc.x0, y0 = tc.y0;
+      const bool interior = (y0 >= PB) && (y0 + PT_H + PA <= h) && (x0 >= PB) && (x0 + PT_W + PA <= w);
+      float* sRc = sRc0 + (k & 1) * RC_FLOATS;
+      if (!interior) {                      // tile-uniform: all consumers take the same branch
+        if (ctid < PT_W) {
+          const int gx = min(x0 + ctid, w - 1);
+          sRc[ctid] = __fdiv_rn(1.0f, (float)(min(gx + PA, w - 1) - max(gx - PB, 0) + 1));
+        } else if (ctid < PT_W + PT_H) {
+          const int gy = min(y0 + ctid - PT_W, h - 1);
+          sRc[ctid] = __fdiv_rn(1.0f, (float)(min(gy + PA, h - 1) - max(gy - PB, 0) + 1));
+        }
+        named_bar_sync(2, NCONS);
+      }
+      const int gy = y0 + r;
+      const bool rowok = gy < h;
+      float hold[2][8];                     // odd pixels: channels 4..7 of the previous unit (lanes 4..7)
+      for (int u = 0; u < units; ++u, ++q) {
+        const unsigned s = q % NSTAGE, uu = q / NSTAGE;
+        const float* sV = sV0 + s * SV_FLOATS;
+        const int nchu = min(UC, C - u * UC);
+        const bool last = (u == units - 1);
+        mbar_wait(bars + s, uu & 1u);       // producers filled this stage
+        const bool active = f < nchu;
+        const int phase = (u == 0) ? 0 : (last ? 2 : 1);
+#pragma unroll
+        for (int xi = 0; xi < 2; ++xi) {
+          const int xb = xbh * 2 + xi;
+          const int gx0 = x0 + xb * 16;
+          const float* vline = sV + (r * UC + f) * VPITCH + xb * 16;
+          float* o = out + (((long long)tc.n * h + gy) * w + gx0) * C + u * UC + f;
+          float* hp = sHead + (r * 4 + xb) * 32 + (f & 3);
+          const int wleft = w - gx0;
+#define SHDR_CONSUME(I, P) consume_block<CT, EO, I, P>(vline, o, hp, hold[xi], sRc, r, xb, f, u, C, active, rowok, wleft, prm.dbg)
+          if (interior) {
+            if (phase == 0) SHDR_CONSUME(true, 0); else if (phase == 1) SHDR_CONSUME(true, 1); else SHDR_CONSUME(true, 2);
+          } else {
+            if (phase == 0) SHDR_CONSUME(false, 0); else if (phase == 1) SHDR_CONSUME(false, 1); else SHDR_CONSUME(false, 2);
+          }
+#undef SHDR_CONSUME
+        }
+        if (EO && u == 0) __syncwarp();     // sHead: written by lanes 0..3, read by lanes 4..7 of the same warp
+        mbar_arrive(bars + NSTAGE + s);     // this thread is done reading sV[s]
+      }
+    }
+  }
+}
+
+template <int CT, bool EO>
+static int launch_t(const float* img, float* out, const Params& prm, int sms, cudaStream_t st) {
+  SHDR_CUDA(cudaFuncSetAttribute(k_hist_pooled_ws<CT, EO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)SMEM_BYTES));
+  const int grid = prm.tiles_total < sms ? prm.tiles_total : sms;
+  k_hist_pooled_ws<CT, EO><<<grid, THREADS, SMEM_BYTES, st>>>(img, out, prm);
+  SHDR_LAUNCH_CHECK("k_hist_pooled_ws");
+  return SHDR_OK;
+}
+}  // namespace ws
+
+// true when the warp-specialised kernel can run this request
+bool hist_pooled_ws_supported(int w, const int* bins, int nbins, int ostride, int ooff) {
+  int C = 0;
+  for (int i = 0; i < nbins; ++i) {
+    if (bins[i] < 4 || (bins[i] & (bins[i] - 1)) != 0) return false;   // power-of-two B >= 4 only
+    C += 3 * bins[i];
+  }
+  return C <= ws::MAXC && ostride == C && ooff == 0 && (w % 2) == 0;
+}
+
+int launch_hist_pooled_ws(const float* img, float* out, int n, int h, int w, const int* bins, int nbins, int dev,
+                          cudaStream_t st) {
+  ws::Params p;
+  int C = 0;
+  for (int i = 0; i < nbins; ++i) {
+    const int B = bins[i];
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < 3; ++c) {
+        p.centre[C] = (float)(2 * b + 1) / (float)(2 * B);   // exact for power-of-two B
+        p.nbins[C] = (float)B;
+        p.col[C] = (unsigned char)c;
+        ++C;
+      }
+  }
+  for (int i = C; i < ws::MAXC; ++i) { p.centre[i] = 0.f; p.nbins[i] = 1.f; p.col[i] = 0; }
+  p.C = C;
+  p.n = n; p.h = h; p.w = w;
+  p.tiles_x = (w + ws::PT_W - 1) / ws::PT_W;
+  p.tiles_y = (h + ws::PT_H - 1) / ws::PT_H;
+  const long long total = (long long)n * p.tiles_x * p.tiles_y;
+  SHDR_REQUIRE(total > 0 && total < 0x7fffffffLL, "hist_pooled_ws: %lld tiles out of range", total);
+  p.tiles_total = (int)total;
+  { const char* e = getenv("SHDR_POOL_DBG"); p.dbg = e ? atoi(e) : 0; }
+  const int sms = sm_count(dev);
+  switch (C) {
+    case 84: return ws::launch_t<84, true>(img, out, p, sms, st);    // B = 4, 8, 16
+    case 12: return ws::launch_t<12, true>(img, out, p, sms, st);    // B = 4
+    case 24: return ws::launch_t<24, false>(img, out, p, sms, st);   // B = 8
+    case 48: return ws::launch_t<48, false>(img, out, p, sms, st);   // B = 16
+    default: break;
+  }
+  return (C % 8 == 4) ? ws::launch_t<0, true>(img, out, p, sms, st) : ws::launch_t<0, false>(img, out, p, sms, st);
+}
+
+}  // namespace shdr
