@@ -82,6 +82,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// vote / 256 = max(fma(-|v - c|, B/256, 1/256), 0).  Scaling by a power of two commutes with every rounding that
+// follows (no under/overflow: the smallest non-zero vote is 2^-24), so all window sums are exactly 1/256 of the
+// un-scaled ones and interior tiles need no multiply at all.
+__device__ __forceinline__ float vote256(float v, float centre, float nbs) {
+  return fmaxf(fmaf(-fabsf(__fsub_rn(v, centre)), nbs, 1.0f / 256.0f), 0.0f);
+}
+
 struct TileCoord { int n, y0, x0; };
 __device__ __forceinline__ TileCoord tile_coord(int t, const Params& p) {
   TileCoord c;
@@ -141,9 +148,9 @@ __device__ __forceinline__ void consume_block(const float* __restrict__ vline, f
   }
   float res[16];
   if (INTERIOR) {
-    res[0] = a[0] * (1.0f / 256.0f);       // exact: power-of-two count
+    res[0] = a[0];                          // votes arrive pre-scaled by the exact 1/256 (see vote256)
 #pragma unroll
-    for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(a[j], a[15 + j]) * (1.0f / 256.0f);
+    for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(a[j], a[15 + j]);
   } else {
     const float rcy = sRc[PT_W + r];
     const float4* rc4 = reinterpret_cast<const float4*>(sRc + xb * 16);
@@ -155,7 +162,7 @@ __device__ __forceinline__ void consume_block(const float* __restrict__ vline, f
       for (int e = 0; e < 4; ++e) {
         const int j = 4 * qd + e;
         const float sum = (j == 0) ? a[0] : __fadd_rn(a[j], a[15 + j]);
-        res[j] = sum * (rcy * sc[e]);      // <= 2 ulp from sum / (rows * cols)
+        res[j] = sum * (256.0f * (rcy * sc[e]));   // undo the 1/256; <= 2 ulp from sum / (rows * cols)
       }
     }
   }
@@ -167,6 +174,7 @@ __device__ __forceinline__ void consume_block(const float* __restrict__ vline, f
     return;
   }
   const bool lo = f < 4;
+  float* const ohold = lo ? o : o - UC;    // odd pixels: lanes 4..7 store 8 channels back (the held ones)
   if (!EO) {
     if (active) {
 #pragma unroll
@@ -188,13 +196,13 @@ __device__ __forceinline__ void consume_block(const float* __restrict__ vline, f
     } else if (PHASE == 1) {
       if (ok) {
         st_stream1(oe, res[je]);
-        st_stream1(lo ? oo : oo - UC, lo ? res[jo] : hold[jp]);
+        st_stream1(ohold + jo * C, lo ? res[jo] : hold[jp]);
       }
       hold[jp] = res[jo];
     } else {
       if (ok) {
         st_stream1(lo ? oe : oe + (C - u * UC - 4), lo ? res[je] : hp[jp * 4]);
-        st_stream1(lo ? oo : oo - UC, lo ? res[jo] : hold[jp]);
+        st_stream1(ohold + jo * C, lo ? res[jo] : hold[jp]);
       }
     }
   }
@@ -261,16 +269,16 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
           const int cb = it / IN_W;
           const int xc = it - cb * IN_W;
           const int ch = u * UC + cb;
-          const float centre = sCentre[ch], nb = sNb[ch];
+          const float centre = sCentre[ch], nbs = sNb[ch] * (1.0f / 256.0f);
           const float4* col = reinterpret_cast<const float4*>(sI + (sCol[ch] * IN_W + xc) * IPITCH);
           float a[32];
 #pragma unroll
           for (int qd = 0; qd < 8; ++qd) {
             const float4 v = col[qd];
-            a[4 * qd + 0] = hist_vote_pow2(v.x, centre, nb);
-            a[4 * qd + 1] = hist_vote_pow2(v.y, centre, nb);
-            a[4 * qd + 2] = hist_vote_pow2(v.z, centre, nb);
-            a[4 * qd + 3] = hist_vote_pow2(v.w, centre, nb);
+            a[4 * qd + 0] = vote256(v.x, centre, nbs);
+            a[4 * qd + 1] = vote256(v.y, centre, nbs);
+            a[4 * qd + 2] = vote256(v.z, centre, nbs);
+            a[4 * qd + 3] = vote256(v.w, centre, nbs);
           }
 #pragma unroll
           for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);      // suffix sums, rows 0..15

@@ -117,6 +117,59 @@ def test_histogram_layer_pooled(shdr_gpu, B):
     assert_rel(got, ref, RTOL_POOL)
 
 
+@pytest.mark.parametrize("shape", [(1, 16, 2, 3), (2, 17, 66, 3), (1, 33, 126, 3), (3, 50, 190, 3), (1, 9, 64, 3),
+                                   (1, 64, 62, 3), (1, 31, 256, 3)])
+def test_hist_multi_pooled_ws_tile_edges(shdr_gpu, shape):
+    """Even widths take the warp-specialised whole-sector kernel: partial tiles, 1-tile images, many tiles."""
+    img = rnd(shape, sum(shape) + 7)
+    got = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    assert_rel(got, oracle.hist_multi(img, pool_k=16), RTOL_POOL)
+
+
+@pytest.mark.parametrize("B", [8, 16, 32, 64])
+def test_histogram_layer_pooled_pow2(shdr_gpu, B):
+    """C = 3B channels: 24, 48 (compile-time pitch, every pixel sector-aligned), 96, 192 (runtime pitch)."""
+    img = rnd((2, 35, 130, 3), B)
+    got = shdr_gpu.histogram_layer(shdr_gpu.DeviceArray.from_numpy(img), B, pool=True).numpy()
+    assert_rel(got, oracle.avg_pool_same(oracle.histogram_layer(img, B), 16), RTOL_POOL)
+
+
+def test_pooled_ws_generic_channel_counts(shdr_gpu):
+    """Channel counts other than 84 through the C ABI: C = 60 (4|16: odd half-sector pitch, runtime), C = 36 (4|8)."""
+    from shdr import _native as N
+    img = rnd((2, 40, 96, 3), 77)
+    d = shdr_gpu.DeviceArray.from_numpy(img)
+    for bins in ((4, 16), (4, 8), (8, 16)):
+        C = 3 * sum(bins)
+        out = shdr_gpu.DeviceArray.from_numpy(np.full((2, 40, 96, C), -1, np.float32))
+        off = 0
+        ref = []
+        for B in bins:      # per-histogram calls into channel slices (block kernel) as the reference layout
+            ref.append(oracle.avg_pool_same(oracle.histogram_layer(img, B), 16))
+        ref = np.concatenate(ref, -1)
+        for B in bins:
+            N.check(N.lib.shdr_soft_hist_f32(d.ptr, out.ptr, 2, 40, 96, 3, B, 16, C, off, None))
+            off += 3 * B
+        assert_rel(out.numpy(), ref, RTOL_POOL)
+
+
+def test_pooled_matches_block_kernel_bitwise(shdr_gpu):
+    """The warp-specialised kernel and the generic block kernel sum in the same order: identical interior bits."""
+    import os, subprocess, sys
+    img = rnd((1, 64, 128, 3), 91)
+    a = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import shdr; "
+            "img = np.random.default_rng(91).random((1, 64, 128, 3), dtype=np.float32); "
+            "np.save(sys.argv[1], shdr.hist_multi(shdr.DeviceArray.from_numpy(img), pool=True).numpy())"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    path = "/tmp/shdr_block_kernel.npy"
+    env = dict(os.environ, SHDR_POOL_BLOCK="1")
+    subprocess.run([sys.executable, "-c", code, path], check=True, env=env)
+    b = np.load(path)
+    assert np.array_equal(a[:, 8:-8, 8:-8], b[:, 8:-8, 8:-8])
+    assert_rel(a, b, 1e-6)
+
+
 def test_pooled_sparse_image_zeros_stay_zero(shdr_gpu):
     """A window with no vote must give exactly 0 (pure relative gate)."""
     img = np.full((1, 64, 96, 3), 0.03, np.float32)       # only bins near 0 vote
