@@ -86,8 +86,15 @@ int emor_device_table(int dev, const float** g0, const float** hinv) {
   const size_t bytes = g_tab_host.size() * sizeof(float);
   if (t.ptr == nullptr) SHDR_CUDA(cudaMalloc((void**)&t.ptr, bytes));
   if (t.version != g_tab_version) {
-    // one-time 49 KB upload per device; synchronous so the host vector may change afterwards
-    SHDR_CUDA(cudaMemcpy(t.ptr, g_tab_host.data(), bytes, cudaMemcpyHostToDevice));
+    // one-time 49 KB upload per device (g0, then hinv TRANSPOSED to [11][1024] so that the curve kernel's
+    // per-sample reads are coalesced); synchronous so the host vector may change afterwards
+    std::vector<float> dev_img(g_tab_host.size());
+    memcpy(dev_img.data(), g_tab_host.data(), SHDR_EMOR_SAMPLES * sizeof(float));
+    for (int s = 0; s < SHDR_EMOR_SAMPLES; ++s)
+      for (int j = 0; j < SHDR_EMOR_NCOMP; ++j)
+        dev_img[SHDR_EMOR_SAMPLES + (size_t)j * SHDR_EMOR_SAMPLES + s] =
+            g_tab_host[SHDR_EMOR_SAMPLES + (size_t)s * SHDR_EMOR_NCOMP + j];
+    SHDR_CUDA(cudaMemcpy(t.ptr, dev_img.data(), bytes, cudaMemcpyHostToDevice));
     t.version = g_tab_version;
   }
   *g0 = t.ptr;

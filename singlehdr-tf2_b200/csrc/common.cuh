@@ -46,7 +46,7 @@ struct DeviceGuard {
 
 int sm_count(int dev);
 
-// EMoR table on the current device ([0..1023] g0, then hinv [1024][11]); nullptr + error if unset.
+// EMoR table on the current device ([0..1023] g0, then hinv TRANSPOSED [11][1024]); error if unset.
 int emor_device_table(int dev, const float** g0, const float** hinv);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -45,6 +45,9 @@ k_curve(const float* __restrict__ w, const float* __restrict__ rf_in,
   __shared__ float bcast[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long item = blockIdx.x;
+  // programmatic dependent launch: the apply kernel that follows in shdr_linearize_f32 may start its CTAs now;
+  // it blocks in griddepcontrol.wait until this grid has completed and its curves are visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (w != nullptr) {
     float wj[SHDR_EMOR_NCOMP];
@@ -53,7 +56,7 @@ k_curve(const float* __restrict__ w, const float* __restrict__ rf_in,
     for (int s = tid; s < k; s += CURVE_THREADS) {
       float acc = 0.0f;                   // matmul row: 11-deep dot, j ascending (:246-249)
 #pragma unroll
-      for (int j = 0; j < SHDR_EMOR_NCOMP; ++j) acc = fmaf(hinv[s * SHDR_EMOR_NCOMP + j], wj[j], acc);
+      for (int j = 0; j < SHDR_EMOR_NCOMP; ++j) acc = fmaf(hinv[j * SHDR_EMOR_SAMPLES + s], wj[j], acc);   // hinv is [11][1024] on the device
       v[s] = __fadd_rn(g0[s], acc);       // G0 + matmul(...)
     }
   } else {
@@ -180,6 +183,7 @@ k_apply_rf(const float* __restrict__ x, const float* __restrict__ rf, float* __r
   const long long item = blockIdx.x / chunks_per_item;
   const int chunk = blockIdx.x - (int)(item * chunks_per_item);
   const float* r = rf + item * k;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent of k_curve
   if (SMEM) {
     for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
     __syncthreads();
@@ -224,7 +228,7 @@ k_apply_rf(const float* __restrict__ x, const float* __restrict__ rf, float* __r
 
 template <bool SMEM, bool VEC>
 static int launch_apply_t(const float* x, const float* rf, float* y, int b, long long n, int k,
-                          cudaStream_t st, int dev) {
+                          cudaStream_t st, int dev, bool pdl) {
   // chunk: multiple of 4 * threads * unroll elements; shrink until the grid has >= 8 CTAs per SM
   const long long quantum = 4LL * APPLY_THREADS * APPLY_UNROLL;   // 4096 elements
   long long per_chunk = quantum * 8;                              // 32768 elements = 128 KB in
@@ -236,19 +240,29 @@ static int launch_apply_t(const float* x, const float* rf, float* y, int b, long
   size_t smem = SMEM ? (size_t)k * sizeof(float2) : 0;
   if (smem > 48 * 1024)
     SHDR_CUDA(cudaFuncSetAttribute(k_apply_rf<SMEM, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_apply_rf<SMEM, VEC><<<(unsigned)grid, APPLY_THREADS, smem, st>>>(x, rf, y, n, k, (int)chunks, per_chunk);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(APPLY_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;      // overlap this launch with the tail of the curve kernel before it
+  SHDR_CUDA(cudaLaunchKernelEx(&cfg, k_apply_rf<SMEM, VEC>, x, rf, y, n, k, (int)chunks, per_chunk));
   SHDR_LAUNCH_CHECK("k_apply_rf");
   return SHDR_OK;
 }
 
 static int launch_apply(const float* x, const float* rf, float* y, int b, long long n, int k,
-                        cudaStream_t st, int dev) {
+                        cudaStream_t st, int dev, bool pdl = false) {
   const bool vec = (n % 4 == 0) && aligned16(x) && aligned16(y);
   const bool smem = (size_t)k * sizeof(float2) <= 200 * 1024;
-  if (smem) return vec ? launch_apply_t<true, true>(x, rf, y, b, n, k, st, dev)
-                       : launch_apply_t<true, false>(x, rf, y, b, n, k, st, dev);
-  return vec ? launch_apply_t<false, true>(x, rf, y, b, n, k, st, dev)
-             : launch_apply_t<false, false>(x, rf, y, b, n, k, st, dev);
+  if (smem) return vec ? launch_apply_t<true, true>(x, rf, y, b, n, k, st, dev, pdl)
+                       : launch_apply_t<true, false>(x, rf, y, b, n, k, st, dev, pdl);
+  return vec ? launch_apply_t<false, true>(x, rf, y, b, n, k, st, dev, pdl)
+             : launch_apply_t<false, false>(x, rf, y, b, n, k, st, dev, pdl);
 }
 
 }  // namespace shdr
@@ -293,5 +307,5 @@ extern "C" int shdr_linearize_f32(const float* x, const float* w, float* y, floa
   if (g.status != SHDR_OK) return g.status;
   int rc = launch_curve(w, nullptr, curve_out, b, SHDR_EMOR_SAMPLES, 1, (cudaStream_t)stream, g.dev);
   if (rc != SHDR_OK || elems_per_item == 0) return rc;
-  return launch_apply(x, curve_out, y, b, elems_per_item, SHDR_EMOR_SAMPLES, (cudaStream_t)stream, g.dev);
+  return launch_apply(x, curve_out, y, b, elems_per_item, SHDR_EMOR_SAMPLES, (cudaStream_t)stream, g.dev, true);
 }
