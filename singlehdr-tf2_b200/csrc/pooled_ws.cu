@@ -120,52 +120,15 @@ __device__ __forceinline__ void stage_tile(float* sI, const float* __restrict__ 
   }
 }
 
-// One consumer thread, one 16-column block of one unit: horizontal 16-window sums of its (row, channel) line,
-// scale, and whole-sector stores.  INTERIOR (tile-uniform) removes every bounds test and uses the exact 1/256;
-// PHASE (unit-uniform): 0 = first unit, 1 = middle, 2 = last unit.
+// Whole-sector stores of 16 consecutive output columns of one (row, channel) lane.  o points at this lane's
+// channel of the first pixel.  INTERIOR (tile-uniform) removes every bounds test; PHASE (unit-uniform):
+// 0 = first unit, 1 = middle, 2 = last unit.
 //   even pixel (sector-aligned): its 8 fresh channels are one sector; at the last unit (4 channels) lanes 4..7
 //     store the odd right neighbour's first 4 channels, parked in shared memory since unit 0 by lanes 0..3;
 //   odd pixel: {4 channels held from the previous unit (lanes 4..7), 4 fresh channels (lanes 0..3)} are one sector.
 template <int CT, bool EO, bool INTERIOR, int PHASE>
-__device__ __forceinline__ void consume_block(const float* __restrict__ vline, float* __restrict__ o, float* hp,
-                                              float (&hold)[8], const float* __restrict__ sRc, int r, int xb,
-                                              int f, int u, int C, bool active, bool rowok, int wleft, int dbg) {
-  float a[32];
-  if (active) {
-    const float4* vl = reinterpret_cast<const float4*>(vline);
-#pragma unroll
-    for (int qd = 0; qd < 8; ++qd) {
-      const float4 v = vl[qd];
-      a[4 * qd + 0] = v.x; a[4 * qd + 1] = v.y; a[4 * qd + 2] = v.z; a[4 * qd + 3] = v.w;
-    }
-#pragma unroll
-    for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);     // suffix sums, cols 0..15
-#pragma unroll
-    for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);     // prefix sums, cols 16..30
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) a[i] = 0.0f;
-  }
-  float res[16];
-  if (INTERIOR) {
-    res[0] = a[0];                          // votes arrive pre-scaled by the exact 1/256 (see vote256)
-#pragma unroll
-    for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(a[j], a[15 + j]);
-  } else {
-    const float rcy = sRc[PT_W + r];
-    const float4* rc4 = reinterpret_cast<const float4*>(sRc + xb * 16);
-#pragma unroll
-    for (int qd = 0; qd < 4; ++qd) {
-      const float4 v = rc4[qd];
-      const float sc[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = 4 * qd + e;
-        const float sum = (j == 0) ? a[0] : __fadd_rn(a[j], a[15 + j]);
-        res[j] = sum * (256.0f * (rcy * sc[e]));   // undo the 1/256; <= 2 ulp from sum / (rows * cols)
-      }
-    }
-  }
+__device__ __forceinline__ void emit16(const float (&res)[16], float* __restrict__ o, float* hp, float (&hold)[8],
+                                       int f, int u, int C, bool active, bool rowok, int wleft, int dbg) {
   if (dbg == 1) {                          // experiment: no global stores (kept live by an impossible predicate)
     float acc = 0.0f;
 #pragma unroll
@@ -188,7 +151,6 @@ __device__ __forceinline__ void consume_block(const float* __restrict__ vline, f
     const int je = 2 * jp, jo = je + 1;
     const bool ok = INTERIOR || (rowok && je < wleft);     // w is even: the pair is in or out together
     float* oe = o + je * C;
-    float* oo = o + jo * C;
     if (PHASE == 0) {
       if (ok) st_stream1(oe, res[je]);
       if (lo) hp[jp * 4] = res[jo];                        // park channels 0..3 of the odd pixel
@@ -206,6 +168,71 @@ __device__ __forceinline__ void consume_block(const float* __restrict__ vline, f
       }
     }
   }
+}
+
+// scale 16 window sums: interior tiles need nothing (votes are pre-scaled by the exact 1/256, see vote256)
+template <bool INTERIOR>
+__device__ __forceinline__ void scale16(float (&res)[16], const float* __restrict__ sRc, int r, int xb) {
+  if (INTERIOR) return;
+  const float rcy = 256.0f * sRc[PT_W + r];                // undo the 1/256 (exact)
+  const float4* rc4 = reinterpret_cast<const float4*>(sRc + xb * 16);
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    const float4 v = rc4[qd];
+    res[4 * qd + 0] *= rcy * v.x;                          // <= 2 ulp from sum / (rows * cols)
+    res[4 * qd + 1] *= rcy * v.y;
+    res[4 * qd + 2] *= rcy * v.z;
+    res[4 * qd + 3] *= rcy * v.w;
+  }
+}
+
+// One consumer thread, TWO adjacent 16-column blocks of one unit: the 32 horizontal 16-window sums of its
+// (row, channel) line from 47 column sums (12 LDS.128), chained van Herk: blocks A = cols 0..15, B = 16..31,
+// C = 32..46;  out[j] = suffixA[j] + prefixB[j-1] (j < 16),  out[16+j] = suffixB[j] + prefixC[j-1].
+template <int CT, bool EO, bool INTERIOR, int PHASE>
+__device__ __forceinline__ void consume_pair(const float* __restrict__ vline, float* __restrict__ o, float* hp,
+                                             float (&hold)[2][8], const float* __restrict__ sRc, int r, int xb0,
+                                             int f, int u, int C, bool active, bool rowok, int wleft, int dbg) {
+  const float4* vl = reinterpret_cast<const float4*>(vline);
+  float a[32], bs[16], res[16];
+  if (active) {
+#pragma unroll
+    for (int qd = 0; qd < 8; ++qd) {
+      const float4 v = vl[qd];
+      a[4 * qd + 0] = v.x; a[4 * qd + 1] = v.y; a[4 * qd + 2] = v.z; a[4 * qd + 3] = v.w;
+    }
+    bs[15] = a[31];
+#pragma unroll
+    for (int i = 14; i >= 0; --i) bs[i] = __fadd_rn(a[16 + i], bs[i + 1]);   // suffix sums of B
+#pragma unroll
+    for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);          // suffix sums of A
+#pragma unroll
+    for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);          // prefix sums of B (to col 30)
+    res[0] = a[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(a[j], a[15 + j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { res[j] = 0.0f; bs[j] = 0.0f; }
+  }
+  scale16<INTERIOR>(res, sRc, r, xb0);
+  emit16<CT, EO, INTERIOR, PHASE>(res, o, hp, hold[0], f, u, C, active, rowok, wleft, dbg);
+
+  if (active) {
+    float c[16];
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+      const float4 v = vl[8 + qd];                         // cols 32..47 (47 is padding, never used)
+      c[4 * qd + 0] = v.x; c[4 * qd + 1] = v.y; c[4 * qd + 2] = v.z; c[4 * qd + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 1; i < 15; ++i) c[i] = __fadd_rn(c[i], c[i - 1]);           // prefix sums of C
+    res[0] = bs[0];
+#pragma unroll
+    for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(bs[j], c[j - 1]);
+  }
+  scale16<INTERIOR>(res, sRc, r, xb0 + 1);
+  emit16<CT, EO, INTERIOR, PHASE>(res, o + 16 * C, hp + 32, hold[1], f, u, C, active, rowok, wleft - 16, dbg);
 }
 
 // EO: C == 4 (mod 8) -> pixel pitch is an odd number of half-sectors, even/odd pixels alternate alignment.
@@ -265,29 +292,45 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
         float* sV = sV0 + s * SV_FLOATS;
         mbar_wait(bars + NSTAGE + s, (uu & 1u) ^ 1u);   // consumers released this stage (passes at once on first use)
         const int nchu = min(UC, C - u * UC);
-        for (int it = ptid; it < IN_W * nchu; it += NPROD) {
-          const int cb = it / IN_W;
-          const int xc = it - cb * IN_W;
-          const int ch = u * UC + cb;
-          const float centre = sCentre[ch], nbs = sNb[ch] * (1.0f / 256.0f);
-          const float4* col = reinterpret_cast<const float4*>(sI + (sCol[ch] * IN_W + xc) * IPITCH);
-          float a[32];
+        // An item is (column, two channels).  Channels p and p+3 of a unit read the same colour plane, so the pair
+        // shares ONE fetch of the 31-row input column (8 LDS.128); the two left-over channels of the unit form a
+        // mixed pair that re-fetches.  8 channels: (0,3) (1,4) (2,5) (6,7);  4 channels: (0,3) (1,2).
+        const int nent = nchu >> 1;
+        for (int it = ptid; it < IN_W * nent; it += NPROD) {
+          const int e = it / IN_W;
+          const int xc = it - e * IN_W;
+          int cbA, cbB;
+          if (nchu == UC) { cbA = (e < 3) ? e : 6; cbB = (e < 3) ? e + 3 : 7; }
+          else            { cbA = e;               cbB = e ? 2 : 3; }
+          float I[32];
+          int colour = -1;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int cb = half ? cbB : cbA;
+            const int ch = u * UC + cb;
+            const int cl = sCol[ch];
+            if (cl != colour) {              // warp-uniform except where a warp straddles two entries
+              colour = cl;
+              const float4* col = reinterpret_cast<const float4*>(sI + (cl * IN_W + xc) * IPITCH);
 #pragma unroll
-          for (int qd = 0; qd < 8; ++qd) {
-            const float4 v = col[qd];
-            a[4 * qd + 0] = vote256(v.x, centre, nbs);
-            a[4 * qd + 1] = vote256(v.y, centre, nbs);
-            a[4 * qd + 2] = vote256(v.z, centre, nbs);
-            a[4 * qd + 3] = vote256(v.w, centre, nbs);
+              for (int qd = 0; qd < 8; ++qd) {
+                const float4 v = col[qd];
+                I[4 * qd + 0] = v.x; I[4 * qd + 1] = v.y; I[4 * qd + 2] = v.z; I[4 * qd + 3] = v.w;
+              }
+            }
+            const float centre = sCentre[ch], nbs = sNb[ch] * (1.0f / 256.0f);
+            float a[31];
+#pragma unroll
+            for (int i = 0; i < 31; ++i) a[i] = vote256(I[i], centre, nbs);
+#pragma unroll
+            for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);      // suffix sums, rows 0..15
+#pragma unroll
+            for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);      // prefix sums, rows 16..30
+            float* vcol = sV + cb * VPITCH + xc;
+            vcol[0] = a[0];
+#pragma unroll
+            for (int r = 1; r < 16; ++r) vcol[r * (UC * VPITCH)] = __fadd_rn(a[r], a[15 + r]);
           }
-#pragma unroll
-          for (int i = 14; i >= 0; --i) a[i] = __fadd_rn(a[i], a[i + 1]);      // suffix sums, rows 0..15
-#pragma unroll
-          for (int i = 17; i < 31; ++i) a[i] = __fadd_rn(a[i], a[i - 1]);      // prefix sums, rows 16..30
-          float* vcol = sV + cb * VPITCH + xc;
-          vcol[0] = a[0];
-#pragma unroll
-          for (int r = 1; r < 16; ++r) vcol[r * (UC * VPITCH)] = __fadd_rn(a[r], a[15 + r]);
         }
         mbar_arrive(bars + s);             // release: this thread's column sums are in sV[s]
       }
@@ -327,15 +370,14 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
         mbar_wait(bars + s, uu & 1u);       // producers filled this stage
         const bool active = f < nchu;
         const int phase = (u == 0) ? 0 : (last ? 2 : 1);
-#pragma unroll
-        for (int xi = 0; xi < 2; ++xi) {
-          const int xb = xbh * 2 + xi;
-          const int gx0 = x0 + xb * 16;
-          const float* vline = sV + (r * UC + f) * VPITCH + xb * 16;
+        {
+          const int xb0 = xbh * 2;
+          const int gx0 = x0 + xb0 * 16;
+          const float* vline = sV + (r * UC + f) * VPITCH + xb0 * 16;
           float* o = out + (((long long)tc.n * h + gy) * w + gx0) * C + u * UC + f;
-          float* hp = sHead + (r * 4 + xb) * 32 + (f & 3);
+          float* hp = sHead + (r * 4 + xb0) * 32 + (f & 3);
           const int wleft = w - gx0;
-#define SHDR_CONSUME(I, P) consume_block<CT, EO, I, P>(vline, o, hp, hold[xi], sRc, r, xb, f, u, C, active, rowok, wleft, prm.dbg)
+#define SHDR_CONSUME(I, P) consume_pair<CT, EO, I, P>(vline, o, hp, hold, sRc, r, xb0, f, u, C, active, rowok, wleft, prm.dbg)
           if (interior) {
             if (phase == 0) SHDR_CONSUME(true, 0); else if (phase == 1) SHDR_CONSUME(true, 1); else SHDR_CONSUME(true, 2);
           } else {
