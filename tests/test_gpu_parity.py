@@ -378,3 +378,34 @@ def test_streams_and_events(shdr_gpu):
     assert e0.elapsed_ms(e1) >= 0
     s.sync()
     assert np.array_equal(out.numpy(), oracle.frontend(img))
+
+
+# ---------------------------------------------------------------- out-of-bounds canaries (compute-sanitizer is closed on this pool)
+@pytest.mark.parametrize("shape", [(2, 40, 130, 3), (1, 19, 33, 3), (1, 16, 64, 3), (3, 17, 2, 3)])
+def test_no_writes_outside_the_output(shdr_gpu, shape):
+    """Every kernel writes its output and nothing else: guard bands before and after the tensor stay intact."""
+    from shdr import _native as N
+    n, h, w, _ = shape
+    img = rnd(shape, 123 + w)
+    d_img = shdr_gpu.DeviceArray.from_numpy(img)
+    wts = np.random.default_rng(5).normal(0, 0.5, (n, 11)).astype(np.float32)
+    d_w = shdr_gpu.DeviceArray.from_numpy(wts)
+    G = 4096                                  # guard floats on each side (16 KB, keeps 16-byte alignment)
+
+    def run(nfloats, launch):
+        buf = shdr_gpu.DeviceArray.from_numpy(np.full(nfloats + 2 * G, -7.0, np.float32))
+        launch(buf.ptr + 4 * G)
+        got = buf.numpy()
+        assert (got[:G] == -7.0).all() and (got[-G:] == -7.0).all(), "kernel wrote outside its output tensor"
+        assert not (got[G:-G] == -7.0).any(), "kernel left output elements unwritten"
+        return got[G:-G]
+
+    px = n * h * w
+    fe = run(px * 93, lambda p: N.check(N.lib.shdr_frontend_f32(d_img.ptr, p, n, h, w, 0, None)))
+    assert np.array_equal(fe.reshape(n, h, w, 93), oracle.frontend(img))
+    hp = run(px * 84, lambda p: N.check(N.lib.shdr_hist_multi_f32(d_img.ptr, p, n, h, w, 16, None)))
+    assert_rel(hp.reshape(n, h, w, 84), oracle.hist_multi(img, pool_k=16), RTOL_POOL)
+    fp = run(px * 93, lambda p: N.check(N.lib.shdr_frontend_f32(d_img.ptr, p, n, h, w, 16, None)))
+    assert_rel(fp.reshape(n, h, w, 93)[..., 9:], oracle.hist_multi(img, pool_k=16), RTOL_POOL)
+    curve = shdr_gpu.DeviceArray.empty((n, 1024))
+    run(px * 3, lambda p: N.check(N.lib.shdr_linearize_f32(d_img.ptr, d_w.ptr, p, curve.ptr, n, h * w * 3, None)))
