@@ -224,7 +224,7 @@ int launch_hist_pooled(const float* img, float* out, int n, int h, int w, const 
                        int ostride, int ooff, cudaStream_t st) {
   // fast path: power-of-two B, dense output, even width -> warp-specialised whole-sector kernel (pooled_ws.cu)
   static const bool force_block = getenv("SHDR_POOL_BLOCK") != nullptr;   // A/B switch for profiling
-  if (!force_block && hist_pooled_ws_supported(w, bins, nbins, ostride, ooff)) {
+  if (!force_block && aligned16(out) && hist_pooled_ws_supported(w, bins, nbins, ostride, ooff)) {   // TMA stores need 16-B alignment
     int dev = 0;
     cudaGetDevice(&dev);
     return launch_hist_pooled_ws(img, out, n, h, w, bins, nbins, dev, st);

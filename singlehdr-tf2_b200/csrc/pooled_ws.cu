@@ -18,7 +18,9 @@
 //       consumers ( 8 warps)  horizontal 16-window sums, scale, whole-sector stores  <- sV[stage]
 //     with mbarrier hand-off and no block-wide barrier; the next tile's input (+halo) is prefetched
 //     with cp.async into the other half of a double-buffered, transposed input tile.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -40,8 +42,14 @@ constexpr int RC_FLOATS = PT_W + PT_H;           // 80
 constexpr int MAXC = 192;                        // up to 64 bins x RGB per launch
 constexpr float SENTINEL = -8.0f;
 constexpr int HEAD_FLOATS = PT_H * (PT_W / 2) * 4;   // odd pixels' channels 0..3, parked from unit 0 to the last unit
+// Output staging for the TMA stores, PER CONSUMER WARP (a warp owns 4 rows x 32 columns x 8 channels of a unit, so
+// only __syncwarp is needed around its bulk stores): EO: [2][16 pixel pairs][4 rows][8 floats] (sector of the even
+// pixels, sector of the odd pixels); !EO: [32 pixels][4 rows][8 floats].  Rows are the INNER dimension so that the
+// 32 lanes of the warp (8 channels x 4 rows) write 128 contiguous bytes: one conflict-free wavefront.
+constexpr int WSTG_FLOATS = 32 * 4 * UC;             // 1024 floats = 4 KB per consumer warp
+constexpr int STG_FLOATS = PT_W * PT_H * UC;         // 8192 floats = 32 KB (must stay first: 128-byte aligned)
 constexpr size_t SMEM_BYTES =
-    (size_t)(2 * SI_FLOATS + NSTAGE * SV_FLOATS + 2 * RC_FLOATS + 3 * MAXC + HEAD_FLOATS) * 4 + 2 * NSTAGE * 8;
+    (size_t)(STG_FLOATS + SI_FLOATS + NSTAGE * SV_FLOATS + 2 * RC_FLOATS + 3 * MAXC + HEAD_FLOATS) * 4 + 2 * NSTAGE * 8;
 
 struct Params {
   float centre[MAXC];        // bin centre of every output channel, fp32 (2i-1)/(2B)
@@ -82,6 +90,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// one sector-aligned box of the staging buffer -> global; coordinates (float, row, pair|pixel, image)
+__device__ __forceinline__ void tma_store4(const CUtensorMap* tmap, const float* smem_src, int c0, int c1, int c2, int c3) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_src);
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+               ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(s) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // vote / 256 = max(fma(-|v - c|, B/256, 1/256), 0).  Scaling by a power of two commutes with every rounding that
 // follows (no under/overflow: the smallest non-zero vote is 2^-24), so all window sums are exactly 1/256 of the
 // un-scaled ones and interior tiles need no multiply at all.
@@ -120,52 +139,38 @@ __device__ __forceinline__ void stage_tile(float* sI, const float* __restrict__ 
   }
 }
 
-// Whole-sector stores of 16 consecutive output columns of one (row, channel) lane.  o points at this lane's
-// channel of the first pixel.  INTERIOR (tile-uniform) removes every bounds test; PHASE (unit-uniform):
-// 0 = first unit, 1 = middle, 2 = last unit.
-//   even pixel (sector-aligned): its 8 fresh channels are one sector; at the last unit (4 channels) lanes 4..7
-//     store the odd right neighbour's first 4 channels, parked in shared memory since unit 0 by lanes 0..3;
+// 16 consecutive output columns of one (row, channel) lane -> the staging buffer, in whole-sector groups.  The
+// stores to HBM are TMA bulk-tensor stores of the staged sectors (issued once per unit by one thread): they do
+// not occupy the LSU data pipe, which is this kernel's limiter, and they clip at the image border by themselves.
+// PHASE (unit-uniform): 0 = first unit, 1 = middle, 2 = last unit (4 channels when EO).
+//   even pixel (sector-aligned): its 8 fresh channels are sector u of the pixel pair; at the last unit lanes 4..7
+//     add the odd neighbour's first 4 channels, parked in shared memory since unit 0 by lanes 0..3;
 //   odd pixel: {4 channels held from the previous unit (lanes 4..7), 4 fresh channels (lanes 0..3)} are one sector.
-template <int CT, bool EO, bool INTERIOR, int PHASE>
-__device__ __forceinline__ void emit16(const float (&res)[16], float* __restrict__ o, float* hp, float (&hold)[8],
-                                       int f, int u, int C, bool active, bool rowok, int wleft, int dbg) {
-  if (dbg == 1) {                          // experiment: no global stores (kept live by an impossible predicate)
-    float acc = 0.0f;
+// stE/stO point at [pair 0 of this 16-column block][row][0] of the warp's staging; a pair is 4 * 8 = 32 floats further.
+template <bool EO, int PHASE>
+__device__ __forceinline__ void emit16(const float (&res)[16], float* __restrict__ stE, float* __restrict__ stO,
+                                       float* hp, float (&hold)[8], int f) {
+  if (!EO) {                               // every pixel is aligned: stE is [pixel][row][8]
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc += res[j];
-    if (acc < -1.0f) o[0] = acc;
+    for (int j = 0; j < 16; ++j) stE[j * (4 * UC) + f] = res[j];
     return;
   }
   const bool lo = f < 4;
-  float* const ohold = lo ? o : o - UC;    // odd pixels: lanes 4..7 store 8 channels back (the held ones)
-  if (!EO) {
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (INTERIOR || (rowok && j < wleft)) st_stream1(o + j * C, res[j]);
-    }
-    return;
-  }
+  const int pos = lo ? f + 4 : f - 4;      // odd pixel: held channels first, fresh channels second
 #pragma unroll
   for (int jp = 0; jp < 8; ++jp) {
     const int je = 2 * jp, jo = je + 1;
-    const bool ok = INTERIOR || (rowok && je < wleft);     // w is even: the pair is in or out together
-    float* oe = o + je * C;
     if (PHASE == 0) {
-      if (ok) st_stream1(oe, res[je]);
+      stE[jp * (4 * UC) + f] = res[je];
       if (lo) hp[jp * 4] = res[jo];                        // park channels 0..3 of the odd pixel
       hold[jp] = res[jo];                                  // lanes 4..7: channels 4..7 wait for the next unit
     } else if (PHASE == 1) {
-      if (ok) {
-        st_stream1(oe, res[je]);
-        st_stream1(ohold + jo * C, lo ? res[jo] : hold[jp]);
-      }
+      stE[jp * (4 * UC) + f] = res[je];
+      stO[jp * (4 * UC) + pos] = lo ? res[jo] : hold[jp];
       hold[jp] = res[jo];
     } else {
-      if (ok) {
-        st_stream1(lo ? oe : oe + (C - u * UC - 4), lo ? res[je] : hp[jp * 4]);
-        st_stream1(ohold + jo * C, lo ? res[jo] : hold[jp]);
-      }
+      stE[jp * (4 * UC) + f] = lo ? res[je] : hp[jp * 4];
+      stO[jp * (4 * UC) + pos] = lo ? res[jo] : hold[jp];
     }
   }
 }
@@ -189,10 +194,10 @@ __device__ __forceinline__ void scale16(float (&res)[16], const float* __restric
 // One consumer thread, TWO adjacent 16-column blocks of one unit: the 32 horizontal 16-window sums of its
 // (row, channel) line from 47 column sums (12 LDS.128), chained van Herk: blocks A = cols 0..15, B = 16..31,
 // C = 32..46;  out[j] = suffixA[j] + prefixB[j-1] (j < 16),  out[16+j] = suffixB[j] + prefixC[j-1].
-template <int CT, bool EO, bool INTERIOR, int PHASE>
-__device__ __forceinline__ void consume_pair(const float* __restrict__ vline, float* __restrict__ o, float* hp,
-                                             float (&hold)[2][8], const float* __restrict__ sRc, int r, int xb0,
-                                             int f, int u, int C, bool active, bool rowok, int wleft, int dbg) {
+template <bool EO, bool INTERIOR, int PHASE>
+__device__ __forceinline__ void consume_pair(const float* __restrict__ vline, float* __restrict__ stE,
+                                             float* __restrict__ stO, float* hp, float (&hold)[2][8],
+                                             const float* __restrict__ sRc, int r, int xb0, int f, bool active) {
   const float4* vl = reinterpret_cast<const float4*>(vline);
   float a[32], bs[16], res[16];
   if (active) {
@@ -216,7 +221,7 @@ __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, fl
     for (int j = 0; j < 16; ++j) { res[j] = 0.0f; bs[j] = 0.0f; }
   }
   scale16<INTERIOR>(res, sRc, r, xb0);
-  emit16<CT, EO, INTERIOR, PHASE>(res, o, hp, hold[0], f, u, C, active, rowok, wleft, dbg);
+  emit16<EO, PHASE>(res, stE, stO, hp, hold[0], f);
 
   if (active) {
     float c[16];
@@ -232,7 +237,7 @@ __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, fl
     for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(bs[j], c[j - 1]);
   }
   scale16<INTERIOR>(res, sRc, r, xb0 + 1);
-  emit16<CT, EO, INTERIOR, PHASE>(res, o + 16 * C, hp + 32, hold[1], f, u, C, active, rowok, wleft - 16, dbg);
+  emit16<EO, PHASE>(res, stE + (EO ? 8 : 16) * (4 * UC), stO + 8 * (4 * UC), hp + 32, hold[1], f);
 }
 
 // EO: C == 4 (mod 8) -> pixel pitch is an odd number of half-sectors, even/odd pixels alternate alignment.
@@ -240,10 +245,12 @@ __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, fl
 // CT: compile-time channel count (pixel pitch in floats) so that store offsets are immediates; 0 = runtime.
 template <int CT, bool EO>
 __global__ void __launch_bounds__(THREADS, 1)
-k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const __grid_constant__ Params prm) {
-  extern __shared__ __align__(16) float smem[];
-  float* sI0 = smem;
-  float* sV0 = smem + 2 * SI_FLOATS;
+k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensorMap tmap,
+                 const __grid_constant__ Params prm) {
+  extern __shared__ __align__(128) float smem[];
+  float* sStage = smem;                    // TMA source: must be 128-byte aligned
+  float* sI = smem + STG_FLOATS;
+  float* sV0 = sI + SI_FLOATS;
   float* sRc0 = sV0 + NSTAGE * SV_FLOATS;
   float* sCentre = sRc0 + 2 * RC_FLOATS;
   float* sNb = sCentre + MAXC;
@@ -267,10 +274,10 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
     sNb[i] = prm.nbins[i];
     sCol[i] = prm.col[i];
   }
-  // pad rows 31..35 of both input buffers hold the sentinel for the whole kernel
-  for (int i = tid; i < 2 * 3 * IN_W * (IPITCH - IN_H); i += THREADS) {
+  // pad rows 31..35 of the input buffer hold the sentinel for the whole kernel
+  for (int i = tid; i < 3 * IN_W * (IPITCH - IN_H); i += THREADS) {
     const int col = i / (IPITCH - IN_H);
-    smem[col * IPITCH + IN_H + (i - col * (IPITCH - IN_H))] = SENTINEL;
+    sI[col * IPITCH + IN_H + (i - col * (IPITCH - IN_H))] = SENTINEL;
   }
   __syncthreads();
 
@@ -278,14 +285,11 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
     // =========================== producers: staging + pass 1 ===========================
     const int ptid = tid;
     int t = blockIdx.x;
-    if (t < prm.tiles_total) stage_tile(sI0, img, tile_coord(t, prm), h, w, ptid);
+    if (t < prm.tiles_total) stage_tile(sI, img, tile_coord(t, prm), h, w, ptid);
     unsigned q = 0;
-    for (int k = 0; t < prm.tiles_total; t += gridDim.x, ++k) {
-      float* sI = sI0 + (k & 1) * SI_FLOATS;
+    for (; t < prm.tiles_total; t += gridDim.x) {
       cp_async_wait_all();
-      named_bar_sync(1, NPROD);          // tile k landed; every producer is done reading the other buffer
-      const int tn = t + gridDim.x;
-      if (tn < prm.tiles_total) stage_tile(sI0 + ((k + 1) & 1) * SI_FLOATS, img, tile_coord(tn, prm), h, w, ptid);
+      named_bar_sync(1, NPROD);          // this tile's input (+halo) has landed
 
       for (int u = 0; u < units; ++u, ++q) {
         const unsigned s = q % NSTAGE, uu = q / NSTAGE;
@@ -334,6 +338,11 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
         }
         mbar_arrive(bars + s);             // release: this thread's column sums are in sV[s]
       }
+      // the input tile is single-buffered (its second copy pays for the TMA staging buffer): refill it once every
+      // producer is done with it; the consumers still have up to NSTAGE units queued, so the ring hides the latency
+      named_bar_sync(1, NPROD);
+      const int tn = t + gridDim.x;
+      if (tn < prm.tiles_total) stage_tile(sI, img, tile_coord(tn, prm), h, w, ptid);
     }
   } else {
     // =========================== consumers: pass 2 + whole-sector stores ===========================
@@ -341,7 +350,15 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
     const int f = ctid & 7;                // channel within the unit == lane within the sector
     const int r = (ctid >> 3) & 15;        // tile row
     const int xbh = ctid >> 7;             // which half of the tile's four 16-column blocks
-    const bool lo = f < 4;
+    const int xb0 = xbh * 2;
+    const int lane = ctid & 31;
+    const int wi = ctid >> 5;              // consumer warp: rows 4*(wi&3) .. +3, column half wi>>2
+    const int rr = r & 3;                  // row within the warp
+    // this warp's staging: [pair | pixel][4 rows][8]; odd-pixel sectors in the second half
+    float* wst = sStage + wi * WSTG_FLOATS;
+    float* stE = wst + rr * UC;
+    float* stO = wst + WSTG_FLOATS / 2 + rr * UC;
+    float* hp = sHead + (r * 4 + xb0) * 32 + (f & 3);
     unsigned q = 0;
     int k = 0;
     for (int t = blockIdx.x; t < prm.tiles_total; t += gridDim.x, ++k) {
@@ -359,45 +376,91 @@ k_hist_pooled_ws(const float* __restrict__ img, float* __restrict__ out, const _
         }
         named_bar_sync(2, NCONS);
       }
-      const int gy = y0 + r;
-      const bool rowok = gy < h;
+      const int ty = y0 + 4 * (wi & 3);     // first row / column of this warp's boxes
+      const int tx = x0 + 32 * xbh;
       float hold[2][8];                     // odd pixels: channels 4..7 of the previous unit (lanes 4..7)
       for (int u = 0; u < units; ++u, ++q) {
         const unsigned s = q % NSTAGE, uu = q / NSTAGE;
         const float* sV = sV0 + s * SV_FLOATS;
         const int nchu = min(UC, C - u * UC);
         const bool last = (u == units - 1);
-        mbar_wait(bars + s, uu & 1u);       // producers filled this stage
         const bool active = f < nchu;
         const int phase = (u == 0) ? 0 : (last ? 2 : 1);
-        {
-          const int xb0 = xbh * 2;
-          const int gx0 = x0 + xb0 * 16;
-          const float* vline = sV + (r * UC + f) * VPITCH + xb0 * 16;
-          float* o = out + (((long long)tc.n * h + gy) * w + gx0) * C + u * UC + f;
-          float* hp = sHead + (r * 4 + xb0) * 32 + (f & 3);
-          const int wleft = w - gx0;
-#define SHDR_CONSUME(I, P) consume_pair<CT, EO, I, P>(vline, o, hp, hold, sRc, r, xb0, f, u, C, active, rowok, wleft, prm.dbg)
-          if (interior) {
-            if (phase == 0) SHDR_CONSUME(true, 0); else if (phase == 1) SHDR_CONSUME(true, 1); else SHDR_CONSUME(true, 2);
-          } else {
-            if (phase == 0) SHDR_CONSUME(false, 0); else if (phase == 1) SHDR_CONSUME(false, 1); else SHDR_CONSUME(false, 2);
-          }
-#undef SHDR_CONSUME
+        // this warp's previous bulk stores must have finished READING its staging before it is overwritten
+        if (lane == 0) tma_wait_read();
+        __syncwarp();
+        mbar_wait(bars + s, uu & 1u);       // producers filled this stage
+        const float* vline = sV + (r * UC + f) * VPITCH + xb0 * 16;
+#define SHDR_CONSUME(I, P) consume_pair<EO, I, P>(vline, stE, stO, hp, hold, sRc, r, xb0, f, active)
+        if (interior) {
+          if (phase == 0) SHDR_CONSUME(true, 0); else if (phase == 1) SHDR_CONSUME(true, 1); else SHDR_CONSUME(true, 2);
+        } else {
+          if (phase == 0) SHDR_CONSUME(false, 0); else if (phase == 1) SHDR_CONSUME(false, 1); else SHDR_CONSUME(false, 2);
         }
-        if (EO && u == 0) __syncwarp();     // sHead: written by lanes 0..3, read by lanes 4..7 of the same warp
+#undef SHDR_CONSUME
         mbar_arrive(bars + NSTAGE + s);     // this thread is done reading sV[s]
+        fence_async_smem();                 // make this thread's staging writes visible to the async (TMA) proxy
+        __syncwarp();                       // the warp's part of the unit is staged (and its parked sHead is visible)
+        if (lane == 0 && prm.dbg != 1) {
+          if (!EO) {
+            tma_store4(&tmap, wst, u * UC, ty, tx, tc.n);                                   // [32 px][4 rows][8 ch]
+          } else {
+            tma_store4(&tmap, wst, u * UC, ty, tx >> 1, tc.n);                              // even pixels: sector u
+            if (u > 0) tma_store4(&tmap, wst + WSTG_FLOATS / 2, C + u * UC - 4, ty, tx >> 1, tc.n);   // odd pixels
+          }
+          tma_commit();
+        }
       }
     }
+    if (lane == 0) tma_wait_all();          // all bulk stores complete before the CTA exits
   }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor map of the output for the per-unit bulk stores.  Dimensions (innermost first): float, row, pixel pair
+// (EO) or pixel (!EO), image -- rows come before pixels so that the staging buffer is [pixel][row][8].
+static int make_tmap(CUtensorMap* tm, float* out, int n, int h, int w, int C, bool eo) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SHDR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    SHDR_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t pitch = (cuuint64_t)C * 4;
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], es[4] = {1, 1, 1, 1};
+  if (eo) {
+    gd[0] = 2 * (cuuint64_t)C; gd[1] = h; gd[2] = w / 2; gd[3] = n;
+    gs[0] = pitch * w; gs[1] = 2 * pitch; gs[2] = pitch * w * h;
+    bx[0] = UC; bx[1] = 4; bx[2] = 16; bx[3] = 1;          // one consumer warp: 4 rows x 16 pixel pairs
+  } else {
+    gd[0] = C; gd[1] = h; gd[2] = w; gd[3] = n;
+    gs[0] = pitch * w; gs[1] = pitch; gs[2] = pitch * w * h;
+    bx[0] = UC; bx[1] = 4; bx[2] = 32; bx[3] = 1;          // one consumer warp: 4 rows x 32 pixels
+  }
+  CUresult rc = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (output must be 16-byte aligned)", (int)rc);
+    return SHDR_ERR_CUDA;
+  }
+  return SHDR_OK;
 }
 
 template <int CT, bool EO>
 static int launch_t(const float* img, float* out, const Params& prm, int sms, cudaStream_t st) {
+  CUtensorMap tm;
+  int rc = make_tmap(&tm, out, prm.n, prm.h, prm.w, prm.C, EO);
+  if (rc != SHDR_OK) return rc;
   SHDR_CUDA(cudaFuncSetAttribute(k_hist_pooled_ws<CT, EO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)SMEM_BYTES));
   const int grid = prm.tiles_total < sms ? prm.tiles_total : sms;
-  k_hist_pooled_ws<CT, EO><<<grid, THREADS, SMEM_BYTES, st>>>(img, out, prm);
+  k_hist_pooled_ws<CT, EO><<<grid, THREADS, SMEM_BYTES, st>>>(img, tm, prm);
   SHDR_LAUNCH_CHECK("k_hist_pooled_ws");
   return SHDR_OK;
 }

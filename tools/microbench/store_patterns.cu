@@ -15,7 +15,8 @@
 
 constexpr int H = 512, W = 512, N = 32, CH = 84, TH = 16, TW = 64;
 
-__global__ void __launch_bounds__(256) k_modes(float* out, int mode, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(256) k_modes(float* out, int mode, const __grid_constant__ CUtensorMap tmap,
+                                               const __grid_constant__ CUtensorMap tmap_pair, int run) {
   extern __shared__ __align__(128) float sm[];
   const int tiles_x = W / TW, tiles_y = H / TH;
   const int tid = threadIdx.x;
@@ -45,6 +46,24 @@ __global__ void __launch_bounds__(256) k_modes(float* out, int mode, const __gri
         for (int i = tid; i < TW * CH / 4; i += 256) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncthreads();
+    }
+    if (mode == 11) {
+      // TMA stores of whole sectors: output viewed as [rows][w/2 pixel pairs][168 floats]; box = (8*run floats,
+      // 32 pairs, 16 rows): `run` aligned sectors of every pixel pair of the tile per bulk store, 21/run passes
+      for (int g = 0; g < 21 / run; ++g) {
+        for (int i = tid; i < TH * (TW / 2) * 8 * run; i += 256) sm[i] = val;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+          const unsigned s = (unsigned)__cvta_generic_to_shared(sm);
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                       ::"l"(&tmap_pair), "r"(g * 8 * run), "r"(x0 / 2), "r"(n * H + y0), "r"(s) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+      }
+      continue;
     }
     if (mode == 10) {
       // 21 passes; pass k writes ONE aligned 32-B sector (sector k of 21) of every pixel pair;
@@ -133,7 +152,18 @@ int main() {
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   printf("tensor map encode rc=%d\n", (int)rc);
-  cudaFuncSetAttribute(k_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, TH * TW * 12 * 4);
+  CUtensorMap tmap_pair[3];
+  int runs[3] = {1, 3, 7};
+  for (int i = 0; i < 3; ++i) {
+    cuuint64_t gd[3] = {2 * CH, W / 2, (cuuint64_t)N * H};
+    cuuint64_t gs[2] = {2 * CH * 4, (cuuint64_t)W * CH * 4};
+    cuuint32_t bx[3] = {(cuuint32_t)(8 * runs[i]), TW / 2, TH};
+    CUresult r2 = ((EncodeFn)fn)(&tmap_pair[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, out, gd, gs, bx, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("pair tensor map (run %d) rc=%d\n", runs[i], (int)r2);
+  }
+  cudaFuncSetAttribute(k_modes, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
   const char* names[11] = {"STG.32 ch x rows (current)", "STG.32 ch x adjacent px", "STG.128 3 lanes/fragment", "TMA box [16][64][12]",
                           "full-line float4 (bound)", "STG.32 84 ch of adjacent px", "prefill full lines + mode 0", "prefill full lines + mode 2", "aligned 96B/pixel-pair, adj pairs", "aligned 96B/pixel-pair, ch x rows", "aligned 32B sectors, 8ch x 4 rows"};
   for (int mode = 0; mode < 11; ++mode) {
@@ -141,13 +171,25 @@ int main() {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
-      k_modes<<<148 * 4, 256, TH * TW * 12 * 4>>>(out, mode, tmap);
+      k_modes<<<148 * 4, 256, TH * TW * 12 * 4>>>(out, mode, tmap, tmap_pair[0], 1);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
     }
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     cudaError_t err = cudaGetLastError();
     printf("mode %d %-32s %.3f ms  %.0f GB/s  %s\n", mode, names[mode], ms, bytes / ms / 1e6, cudaGetErrorString(err));
   }
+  for (int i = 0; i < 3; ++i)
+    for (int ctas : {148, 296}) {
+      cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        k_modes<<<ctas, 256, TH * (TW / 2) * 8 * runs[i] * 4>>>(out, 11, tmap, tmap_pair[i], runs[i]);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+      }
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      printf("mode 11 TMA aligned %3d-byte runs per pixel pair, %3d CTAs  %.3f ms  %.0f GB/s  %s\n", 32 * runs[i], ctas, ms,
+             bytes / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+    }
   float hv[4]; cudaMemcpy(hv, out + 84 * 100 + 13, 4, cudaMemcpyDeviceToHost); printf("sample %.1f\n", hv[0]);
   return 0;
 }
