@@ -15,9 +15,14 @@
 //  2. A block-synchronous two-pass kernel idles at barriers because the passes have different item
 //     counts.  => ONE persistent CTA per SM runs a producer/consumer pipeline over (tile, unit):
 //       producers (10 warps)  votes + vertical 16-window sums  -> column-sum ring sV[3 stages]
-//       consumers ( 8 warps)  horizontal 16-window sums, scale, whole-sector stores  <- sV[stage]
-//     with mbarrier hand-off and no block-wide barrier; the next tile's input (+halo) is prefetched
-//     with cp.async into the other half of a double-buffered, transposed input tile.
+//       consumers ( 8 warps)  horizontal 16-window sums, scale, whole-sector staging + TMA stores  <- sV[stage]
+//     with mbarrier hand-off and no block-wide barrier; the input tile (+halo) is staged transposed with cp.async
+//     (the next one is prefetched into L2 while the current one is processed).
+//  3. With (1) and (2) the LSU/L1 data pipe became the limiter, and every 32-byte sector stored with STG costs one
+//     of its wavefronts.  => each consumer warp stages its results in shared memory with rows innermost (its 32
+//     lanes = 8 channels x 4 rows write 128 contiguous bytes: one conflict-free wavefront) and one lane sends them
+//     to HBM with TMA bulk-tensor stores (cp.async.bulk.tensor.4d, SASS UTMASTG): a 4-D tensor map over
+//     (float, row, pixel pair, image) addresses whole sectors and clips at the image border by itself.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -290,6 +295,21 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
     for (; t < prm.tiles_total; t += gridDim.x) {
       cp_async_wait_all();
       named_bar_sync(1, NPROD);          // this tile's input (+halo) has landed
+      {
+        // pull the NEXT tile's input rows into L2 now, so that the refill of the single input buffer at the end of
+        // this tile is an L2 hit (31 rows x 948 B = 8 lines per row)
+        const int tnx = t + gridDim.x;
+        if (tnx < prm.tiles_total && ptid < IN_H * 8) {
+          const TileCoord nc = tile_coord(tnx, prm);
+          const int rr = ptid >> 3, ln = ptid & 7;
+          const int gy = nc.y0 - PB + rr;
+          const int gx = max(nc.x0 - PB, 0);
+          if (gy >= 0 && gy < h) {
+            const float* p = img + (((long long)nc.n * h + gy) * w + gx) * 3 + ln * 32;
+            if (p < img + (long long)prm.n * h * w * 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+          }
+        }
+      }
 
       for (int u = 0; u < units; ++u, ++q) {
         const unsigned s = q % NSTAGE, uu = q / NSTAGE;
