@@ -14,6 +14,11 @@ order) from the call sites cited in every function, and is anchored on
   (reflect-pad depthwise conv, ``avg_pool2d(count_include_pad=False)``,
   ``cumsum``) -- see ``tests/test_oracle.py``.
 
+Two independent restatements live here and are cross-checked against each other bit for
+bit (``tests/test_oracle_c.py``): ``np_oracle.py`` (NumPy, one full-tensor op per TF op) and
+``shdr_oracle.c`` (plain C, OpenMP; built by ``make -C oracle`` / ``__graft_entry__.build()``,
+wrapped by ``c_oracle.py``; also the CPU baseline that ``bench.py`` times).
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import this package.  The product package
 (``singlehdr-tf2_b200``) never does: it fails loudly when its CUDA library is
