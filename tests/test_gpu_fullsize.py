@@ -5,7 +5,13 @@ import pytest
 
 import oracle
 
+from oracle import c_oracle
+
 pytestmark = pytest.mark.gpu
+
+# The C restatement of the oracle (bit-identical to the NumPy one, tests/test_oracle_c.py) is fast enough to check
+# EVERY element at BASELINE.json's full sizes; without it the NumPy oracle checks one image per configuration.
+HAVE_C = c_oracle.available()
 
 
 def rnd(shape, seed=0):
@@ -23,6 +29,10 @@ def test_config2_pooled_hist_full(shdr_gpu):
         assert np.abs(s - 1).max() < 2e-6          # sum over bins of the pooled votes == 1
     ref = oracle.hist_multi(img[7:8], pool_k=16)
     assert np.all(np.abs(out[7:8] - ref) <= 1e-5 * np.abs(ref))
+    if HAVE_C:                                     # all 32 x 512 x 512 x 84 elements, pure relative gate
+        full = c_oracle.hist_multi(img, pool_k=16)
+        assert np.array_equal(full[7:8], ref)
+        assert np.all(np.abs(out - full) <= 1e-5 * np.abs(full))
 
 
 def test_config3_apply_full(shdr_gpu, emor):
@@ -43,6 +53,9 @@ def test_config3_apply_full(shdr_gpu, emor):
         assert np.all(np.diff(y[b].ravel()[order]) >= -6e-7)      # monotone curve -> order preserved (up to the 3 roundings of the lerp)
     assert np.abs(y[5] - oracle.apply_rf(x[5:6], rc[5:6])[0]).max() <= 1e-5
     assert np.array_equal(y[5], oracle.apply_rf(x[5:6], curve[5:6])[0])   # bit-exact given the same curve
+    if HAVE_C:                                     # every element of the 16 x 1024 x 1024 x 3 batch
+        assert np.abs(y - c_oracle.apply_rf(x, rc)).max() <= 1e-5
+        assert np.array_equal(y, c_oracle.apply_rf(x, curve))
 
 
 def test_config4_frontend_full(shdr_gpu):
@@ -56,6 +69,8 @@ def test_config4_frontend_full(shdr_gpu):
     assert np.array_equal(f[..., 21:45], shdr_gpu.histogram_layer(d, 8).numpy())
     assert np.array_equal(f[..., 45:], shdr_gpu.histogram_layer(d, 16).numpy())
     assert np.array_equal(f[3], oracle.frontend(img[3:4])[0])
+    if HAVE_C:                                     # every element of the 8 x 512 x 512 x 93 tensor, bit for bit
+        assert np.array_equal(f, c_oracle.frontend(img))
 
 
 def test_config5_4k_frame(shdr_gpu, emor):
@@ -67,6 +82,8 @@ def test_config5_4k_frame(shdr_gpu, emor):
     rows = slice(1000, 1016)
     ref = oracle.frontend(img[:, 999:1017])[:, 1:-1]          # interior rows: halo rows are real data
     assert np.array_equal(f[:, rows], ref)
+    if HAVE_C:                                     # the whole 2160 x 3840 x 93 frame, bit for bit
+        assert np.array_equal(f, c_oracle.frontend(img))
     # tile sharding: 4 row tiles with a 1-row read-only halo reproduce the frame
     for (y0, y1, i0, i1) in shdr_gpu.row_tiles(2160, 4, 1, 1)[1:3]:
         part = shdr_gpu.frontend(shdr_gpu.DeviceArray.from_numpy(img[:, i0:i1])).numpy()
