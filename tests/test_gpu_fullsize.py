@@ -92,3 +92,15 @@ def test_config5_4k_frame(shdr_gpu, emor):
     w = np.random.default_rng(99).normal(0, 0.5, (1, 11)).astype(np.float32)
     y, curve = shdr_gpu.linearize(d, shdr_gpu.DeviceArray.from_numpy(w))
     assert np.array_equal(y.numpy()[:, :64], oracle.apply_rf(img[:, :64], curve.numpy()))
+
+
+@pytest.mark.parametrize("shape", [(1, 2160, 3840, 3), (2, 1080, 1922, 3), (1, 1000, 66, 3)])
+def test_pooled_large_frames(shdr_gpu, shape):
+    """Pooled histograms on large / awkward frames (4K; even width that is no multiple of the 64-pixel tile; tall and
+    narrow), every element against the C oracle."""
+    if not HAVE_C:
+        pytest.skip("C oracle not built")
+    img = rnd(shape, 17 + shape[2])
+    out = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    ref = c_oracle.hist_multi(img, pool_k=16)
+    assert np.all(np.abs(out - ref) <= 1e-5 * np.abs(ref))
