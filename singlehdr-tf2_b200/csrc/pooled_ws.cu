@@ -51,8 +51,9 @@ constexpr int HEAD_FLOATS = PT_H * (PT_W / 2) * 4;   // odd pixels' channels 0..
 // only __syncwarp is needed around its bulk stores): EO: [2][16 pixel pairs][4 rows][8 floats] (sector of the even
 // pixels, sector of the odd pixels); !EO: [32 pixels][4 rows][8 floats].  Rows are the INNER dimension so that the
 // 32 lanes of the warp (8 channels x 4 rows) write 128 contiguous bytes: one conflict-free wavefront.
-constexpr int WSTG_FLOATS = 32 * 4 * UC;             // 1024 floats = 4 KB per consumer warp
-constexpr int STG_FLOATS = PT_W * PT_H * UC;         // 8192 floats = 32 KB (must stay first: 128-byte aligned)
+constexpr int WTILE_FLOATS = 16 * 4 * UC;            // one sector of 16 pixel pairs x 4 rows: 512 floats = 2 KB
+constexpr int WSTG_FLOATS = 3 * WTILE_FLOATS;        // per consumer warp: even-pixel tile + two odd-pixel tiles (EO)
+constexpr int STG_FLOATS = (NCONS / 32) * WSTG_FLOATS;   // 12288 floats = 48 KB (must stay first: 128-byte aligned)
 constexpr size_t SMEM_BYTES =
     (size_t)(STG_FLOATS + SI_FLOATS + NSTAGE * SV_FLOATS + 2 * RC_FLOATS + 3 * MAXC + HEAD_FLOATS) * 4 + 2 * NSTAGE * 8;
 
@@ -86,10 +87,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspend up to ~4 us instead of spinning
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n"
-      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity), "r"(4000u) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -144,38 +145,37 @@ __device__ __forceinline__ void stage_tile(float* sI, const float* __restrict__ 
   }
 }
 
-// 16 consecutive output columns of one (row, channel) lane -> the staging buffer, in whole-sector groups.  The
-// stores to HBM are TMA bulk-tensor stores of the staged sectors (issued once per unit by one thread): they do
-// not occupy the LSU data pipe, which is this kernel's limiter, and they clip at the image border by themselves.
+// 16 consecutive output columns of one (row, channel) lane -> the warp's staging tiles, in whole-sector groups.  The
+// stores to HBM are TMA bulk-tensor stores of the staged sectors (issued once per unit by one lane): they do not
+// occupy the LSU data pipe, which is this kernel's limiter, and they clip at the image border by themselves.
 // PHASE (unit-uniform): 0 = first unit, 1 = middle, 2 = last unit (4 channels when EO).
-//   even pixel (sector-aligned): its 8 fresh channels are sector u of the pixel pair; at the last unit lanes 4..7
-//     add the odd neighbour's first 4 channels, parked in shared memory since unit 0 by lanes 0..3;
-//   odd pixel: {4 channels held from the previous unit (lanes 4..7), 4 fresh channels (lanes 0..3)} are one sector.
-// stE/stO point at [pair 0 of this 16-column block][row][0] of the warp's staging; a pair is 4 * 8 = 32 floats further.
+//   even pixel (sector-aligned): its 8 fresh channels are sector u of the pixel pair (tile stE); at the last unit
+//     lanes 4..7 add the odd neighbour's first 4 channels, parked in shared memory since unit 0 by lanes 0..3;
+//   odd pixel: its sector k is {channels 4..7 of unit k-1, channels 0..3 of unit k}: lanes 0..3 complete the CURRENT
+//     odd tile (floats 4..7) and lanes 4..7 start the NEXT one (floats 0..3) -- po is this lane's slot in its tile.
+// stE/po point at [pair 0 of this 16-column block][row][slot]; a pair is 4 rows * 8 = 32 floats further.
 template <bool EO, int PHASE>
-__device__ __forceinline__ void emit16(const float (&res)[16], float* __restrict__ stE, float* __restrict__ stO,
-                                       float* hp, float (&hold)[8], int f) {
+__device__ __forceinline__ void emit16(const float (&res)[16], float* __restrict__ stE, float* __restrict__ po,
+                                       float* hp, int f) {
   if (!EO) {                               // every pixel is aligned: stE is [pixel][row][8]
 #pragma unroll
     for (int j = 0; j < 16; ++j) stE[j * (4 * UC) + f] = res[j];
     return;
   }
   const bool lo = f < 4;
-  const int pos = lo ? f + 4 : f - 4;      // odd pixel: held channels first, fresh channels second
 #pragma unroll
   for (int jp = 0; jp < 8; ++jp) {
     const int je = 2 * jp, jo = je + 1;
     if (PHASE == 0) {
       stE[jp * (4 * UC) + f] = res[je];
       if (lo) hp[jp * 4] = res[jo];                        // park channels 0..3 of the odd pixel
-      hold[jp] = res[jo];                                  // lanes 4..7: channels 4..7 wait for the next unit
+      else po[jp * (4 * UC)] = res[jo];                    // channels 4..7 start odd sector 1
     } else if (PHASE == 1) {
       stE[jp * (4 * UC) + f] = res[je];
-      stO[jp * (4 * UC) + pos] = lo ? res[jo] : hold[jp];
-      hold[jp] = res[jo];
+      po[jp * (4 * UC)] = res[jo];
     } else {
       stE[jp * (4 * UC) + f] = lo ? res[je] : hp[jp * 4];
-      stO[jp * (4 * UC) + pos] = lo ? res[jo] : hold[jp];
+      if (lo) po[jp * (4 * UC)] = res[jo];                 // channels 80..83 complete the last odd sector
     }
   }
 }
@@ -201,8 +201,8 @@ __device__ __forceinline__ void scale16(float (&res)[16], const float* __restric
 // C = 32..46;  out[j] = suffixA[j] + prefixB[j-1] (j < 16),  out[16+j] = suffixB[j] + prefixC[j-1].
 template <bool EO, bool INTERIOR, int PHASE>
 __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, float* __restrict__ stE,
-                                             float* __restrict__ stO, float* hp, float (&hold)[2][8],
-                                             const float* __restrict__ sRc, int r, int xb0, int f, bool active) {
+                                             float* __restrict__ po, float* hp, const float* __restrict__ sRc,
+                                             int r, int xb0, int f, bool active) {
   const float4* vl = reinterpret_cast<const float4*>(vline);
   float a[32], bs[16], res[16];
   if (active) {
@@ -226,7 +226,7 @@ __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, fl
     for (int j = 0; j < 16; ++j) { res[j] = 0.0f; bs[j] = 0.0f; }
   }
   scale16<INTERIOR>(res, sRc, r, xb0);
-  emit16<EO, PHASE>(res, stE, stO, hp, hold[0], f);
+  emit16<EO, PHASE>(res, stE, po, hp, f);
 
   if (active) {
     float c[16];
@@ -242,7 +242,7 @@ __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, fl
     for (int j = 1; j < 16; ++j) res[j] = __fadd_rn(bs[j], c[j - 1]);
   }
   scale16<INTERIOR>(res, sRc, r, xb0 + 1);
-  emit16<EO, PHASE>(res, stE + (EO ? 8 : 16) * (4 * UC), stO + 8 * (4 * UC), hp + 32, hold[1], f);
+  emit16<EO, PHASE>(res, stE + (EO ? 8 : 16) * (4 * UC), po + 8 * (4 * UC), hp + 32, f);
 }
 
 // EO: C == 4 (mod 8) -> pixel pitch is an odd number of half-sectors, even/odd pixels alternate alignment.
@@ -374,10 +374,11 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
     const int lane = ctid & 31;
     const int wi = ctid >> 5;              // consumer warp: rows 4*(wi&3) .. +3, column half wi>>2
     const int rr = r & 3;                  // row within the warp
-    // this warp's staging: [pair | pixel][4 rows][8]; odd-pixel sectors in the second half
+    // this warp's staging: EO: tile 0 = even pixels' sector, tiles 1, 2 = odd pixels' sectors (alternating);
+    // !EO: tiles 0 and 1 together are [32 pixels][4 rows][8]
     float* wst = sStage + wi * WSTG_FLOATS;
     float* stE = wst + rr * UC;
-    float* stO = wst + WSTG_FLOATS / 2 + rr * UC;
+    const bool lo = f < 4;
     float* hp = sHead + (r * 4 + xb0) * 32 + (f & 3);
     unsigned q = 0;
     int k = 0;
@@ -398,7 +399,6 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
       }
       const int ty = y0 + 4 * (wi & 3);     // first row / column of this warp's boxes
       const int tx = x0 + 32 * xbh;
-      float hold[2][8];                     // odd pixels: channels 4..7 of the previous unit (lanes 4..7)
       for (int u = 0; u < units; ++u, ++q) {
         const unsigned s = q % NSTAGE, uu = q / NSTAGE;
         const float* sV = sV0 + s * SV_FLOATS;
@@ -411,7 +411,12 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
         __syncwarp();
         mbar_wait(bars + s, uu & 1u);       // producers filled this stage
         const float* vline = sV + (r * UC + f) * VPITCH + xb0 * 16;
-#define SHDR_CONSUME(I, P) consume_pair<EO, I, P>(vline, stE, stO, hp, hold, sRc, r, xb0, f, active)
+        // odd-pixel tiles: unit u completes tile 1 + (u & 1) (lanes 0..3 -> floats 4..7) and starts the other one
+        // (lanes 4..7 -> floats 0..3)
+        float* ocur = wst + (1 + (u & 1)) * WTILE_FLOATS;
+        float* onext = wst + (2 - (u & 1)) * WTILE_FLOATS;
+        float* po = (lo ? ocur + 4 + f : onext + (f - 4)) + rr * UC;
+#define SHDR_CONSUME(I, P) consume_pair<EO, I, P>(vline, stE, po, hp, sRc, r, xb0, f, active)
         if (interior) {
           if (phase == 0) SHDR_CONSUME(true, 0); else if (phase == 1) SHDR_CONSUME(true, 1); else SHDR_CONSUME(true, 2);
         } else {
@@ -426,7 +431,7 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
             tma_store4(&tmap, wst, u * UC, ty, tx, tc.n);                                   // [32 px][4 rows][8 ch]
           } else {
             tma_store4(&tmap, wst, u * UC, ty, tx >> 1, tc.n);                              // even pixels: sector u
-            if (u > 0) tma_store4(&tmap, wst + WSTG_FLOATS / 2, C + u * UC - 4, ty, tx >> 1, tc.n);   // odd pixels
+            if (u > 0) tma_store4(&tmap, ocur, C + u * UC - 4, ty, tx >> 1, tc.n);   // odd pixels: sector u + C/8
           }
           tma_commit();
         }
