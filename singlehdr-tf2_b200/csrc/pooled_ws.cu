@@ -205,6 +205,7 @@ __device__ __forceinline__ void consume_pair(const float* __restrict__ vline, fl
                                              int r, int xb0, int f, bool active) {
   const float4* vl = reinterpret_cast<const float4*>(vline);
   float a[32], bs[16], res[16];
+  active = (PHASE < 2) || active;          // every unit but the last is full: no inactive lanes to zero there
   if (active) {
 #pragma unroll
     for (int qd = 0; qd < 8; ++qd) {
