@@ -161,6 +161,8 @@ def cpu_step_fn(workload, n_items, h=None):
 def cpu_threads():
     from oracle import c_oracle
     if c_oracle.available():
+        # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1 to its ranks; undo that here)
+        c_oracle.set_threads(int(os.environ.get("SHDR_CPU_THREADS", os.cpu_count() or 1)))
         return c_oracle.threads()
     return max(1, min(os.cpu_count() or 1, 32))
 

@@ -30,6 +30,11 @@ def threads() -> int:
     return int(_l().shdr_oracle_threads())
 
 
+def set_threads(n: int) -> None:
+    """Override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    _l().shdr_oracle_set_threads(int(n))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

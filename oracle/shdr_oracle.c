@@ -22,6 +22,15 @@
 #include <omp.h>
 #endif
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the baseline is meant to use all the host threads it can */
+void shdr_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int shdr_oracle_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
