@@ -87,10 +87,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspend up to ~4 us instead of spinning
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n"
-      "DONE_%=:\n\t}" ::"r"(a), "r"(parity), "r"(4000u) : "memory");
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
