@@ -226,6 +226,10 @@ static int launch_hist_generic(const float* img, float* out, long long npx, int 
   return SHDR_OK;
 }
 
+// pooled_slide.cu
+bool pool_slide_supported(const float* out, int w, const int* bins, int nbins, bool full93);
+int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool full93, int dev, cudaStream_t st);
+
 // pooled.cu
 int launch_hist_pooled(const float* img, float* out, int n, int h, int w, const int* bins, int nbins,
                        int ostride, int ooff, cudaStream_t st);
@@ -309,11 +313,13 @@ extern "C" int shdr_frontend_f32(const float* img, float* out, int n, int h, int
   cudaStream_t st = (cudaStream_t)stream;
   const long long npx = (long long)n * h * w;
   if (pool_k == 0) return launch_strip<true, 7>(img, out, npx, h, w, st);
-  // pooled histograms: img + edges go to channels 0..8, pooled histograms to 9..92
+  // pooled histograms: img + edges go to channels 0..8, pooled histograms to 9..92 -- one launch of the sliding-window
+  // kernel when its per-row bulk copies can be 16-byte aligned (w % 4 == 0), else three generic launches
+  const int bins[3] = {4, 8, 16};
+  if (pool_slide_supported(out, w, bins, 3, true)) return launch_pool_slide(img, out, n, h, w, true, g.dev, st);
   rc = launch_copy_strided(img, out, npx, 3, SHDR_FRONTEND_CH, 0, st, g.dev);
   if (rc != SHDR_OK) return rc;
   rc = launch_sobel_generic(img, out, npx, h, w, 3, SHDR_FRONTEND_CH, 3, st, g.dev);
   if (rc != SHDR_OK) return rc;
-  const int bins[3] = {4, 8, 16};
   return launch_hist_pooled(img, out, n, h, w, bins, 3, SHDR_FRONTEND_CH, 9, st);
 }

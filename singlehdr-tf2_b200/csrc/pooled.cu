@@ -219,16 +219,20 @@ static int launch_pooled_t(const float* img, float* out, int h, int w, int ostri
 bool hist_pooled_ws_supported(int w, const int* bins, int nbins, int ostride, int ooff);
 int launch_hist_pooled_ws(const float* img, float* out, int n, int h, int w, const int* bins, int nbins, int dev,
                           cudaStream_t st);
+bool pool_slide_supported(const float* out, int w, const int* bins, int nbins, bool full93);
+int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool full93, int dev, cudaStream_t st);
 
 int launch_hist_pooled(const float* img, float* out, int n, int h, int w, const int* bins, int nbins,
                        int ostride, int ooff, cudaStream_t st) {
-  // fast path: power-of-two B, dense output, even width -> warp-specialised whole-sector kernel (pooled_ws.cu)
-  static const bool force_block = getenv("SHDR_POOL_BLOCK") != nullptr;   // A/B switch for profiling
-  if (!force_block && aligned16(out) && hist_pooled_ws_supported(w, bins, nbins, ostride, ooff)) {   // TMA stores need 16-B alignment
-    int dev = 0;
-    cudaGetDevice(&dev);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  // 1. the {4, 8, 16} histograms into a dense 84-channel tensor: exact sliding-window kernel (pooled_slide.cu)
+  if (ostride == SHDR_HIST_CH && ooff == 0 && pool_slide_supported(out, w, bins, nbins, false))
+    return launch_pool_slide(img, out, n, h, w, false, dev, st);
+  // 2. power-of-two B, dense output, even width -> warp-specialised whole-sector kernel (pooled_ws.cu);
+  //    its TMA stores need 16-B alignment
+  if (aligned16(out) && hist_pooled_ws_supported(w, bins, nbins, ostride, ooff))
     return launch_hist_pooled_ws(img, out, n, h, w, bins, nbins, dev, st);
-  }
   dim3 grid((w + PT_W - 1) / PT_W, (h + PT_H - 1) / PT_H, n);
   SHDR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "hist_pooled: grid (%u,%u,%u) out of range", grid.x, grid.y, grid.z);
 

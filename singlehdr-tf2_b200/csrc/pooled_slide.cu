@@ -1,0 +1,393 @@
+// pooled_slide.cu -- soft histograms B = {4, 8, 16} fused with the 16x16 stride-1 'same' average pool, as an EXACT
+// integer sliding-window pipeline (the headline kernel, BASELINE.json configs[1]); optionally with img + Sobel in
+// front (the pooled 93-channel front end in ONE launch).
+//
+// Reference behaviour restated (ShinYwings/SingleHDR-tf2): model.histogram_layer, linearization_net.py:336-350, then
+// average_pooling2d(h, 16, 1, 'same'), linearization_net.py:351 (README.md:51): window rows [y-7, y+8], columns
+// [x-7, x+8] clipped to the image, divided by the number of in-bounds elements; concat order of :322.
+//
+// Why integers.  For power-of-two B every vote 1 - |I - c_b|*B is a multiple of 2^-24 in [0, 1] (for I >= c_1 it is
+// exact in fp32), so votes are 25-bit fixed-point numbers and every window sum is an exact
+// 32-bit integer.  Exact sums make a SLIDING window legal (add the entering row, subtract the leaving one -- in fp32
+// the cancellation would destroy the pure-relative 1e-5 tolerance and the "all-zero window stays exactly zero"
+// property), and a sliding window needs only ONE word of state per (column, channel).  That turns the kernel into a
+// stream down the image: no 2-D tile halo to recompute vertically, and every output row of a 64-pixel strip is a
+// single contiguous chunk in HBM (64 x 336 B = 21 KB), sent with one bulk copy -- no partial sectors for any channel
+// count, which is what made the 84-channel tensor awkward for the tiled kernel (pooled_ws.cu).
+//
+// Votes without a vote: with T = rne(I * B * 2^24) and G_b = clamp(T - (b - 1.5) * 2^24, 0, 2^24), the triangular
+// vote of bin b is G_b - G_{b+1}.  G is ONE instruction (DPX VIADDMNMX.RELU: max(min(a + b, c), 0)), and both the
+// clamp and the window sum commute with the difference, so the producers slide B + 1 running sums per (column,
+// colour, B) and difference them when a row is emitted.
+//
+// Pipeline (one persistent CTA per SM, 28 warps, tasks = image x 64-column strip x row segment):
+//   producers (16 warps, one thread per (column incl. 7 + 8 halo, colour, {B4 + B8 | B16})):
+//       global -> T (fixed point) -> private 16-row ring in shared memory (the leaving row's T);
+//       S_b += G_b(T_enter) - G_b(T_leave); column vote sums min(S_b - S_{b+1}, 2^28 - 1) -> stage[channel][column]
+//   consumers (12 warps = 2 row groups x 3 channel groups x 2 half strips, one LANE PER CHANNEL):
+//       47 column sums -> 32 sliding horizontal sums (exact, < 2^32) -> fp32 -> x 1/(count * 2^24) ->
+//       staging[pixel][channel] (lanes = consecutive channels: conflict-free) -> one cp.async.bulk store per row.
+//   (FULL: each consumer lane also computes img + Sobel of one (pixel, colour) of the row into the staging row.)
+// Hand-off through an mbarrier ring of 4 column-sum stages; the two consumer groups alternate rows.
+// All shared-memory traffic is conflict-free by construction (lanes = consecutive columns or consecutive channels;
+// stage pitch 84 = 20 mod 32 words for the 128-bit loads of 8 consecutive channels).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace shdr {
+namespace sl {
+
+constexpr int PK = 16, HL = 7, HR = 8;       // TF SAME: 7 before, 8 after
+constexpr int SW = 64;                       // output columns per strip
+constexpr int CW = SW + HL + HR;             // 79 input columns
+constexpr int NH = 84;                       // histogram channels: 3 * (4 + 8 + 16)
+constexpr int VP = 84;                       // ints per channel line of a stage (79 + pad; 84 = 20 mod 32)
+constexpr int NST = 4;                       // column-sum stages
+constexpr int STAGE_INTS = NH * VP;          // 7056 ints = 28 KB
+constexpr int NPT = 3 * CW;                  // 237 (column, colour) pairs
+constexpr int RING_P = 3 * NPT + 1;          // ints per ring row: T4 | T8 | T16
+constexpr int NPW = 16, NCW = 12;            // producer / consumer warps
+constexpr int NPROD = NPW * 32, NCONS = NCW * 32, THREADS = NPROD + NCONS;
+constexpr int GROUP = NCONS / 2;             // threads of one consumer row group
+constexpr int CAPV = 1 << 24;                // vote 1.0
+constexpr int T_OUT = -(1 << 30);            // "no pixel": every G is 0
+
+template <bool FULL> struct Cfg {
+  static constexpr int CO = FULL ? SHDR_FRONTEND_CH : SHDR_HIST_CH;   // floats per output pixel
+  static constexpr int CH0 = FULL ? 9 : 0;                            // first histogram channel
+  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P + 2 * SW * CO + 2 * SW) * 4 + 2 * NST * 8;
+};
+
+struct Params {
+  const float* img;
+  float* out;
+  int n, h, w;
+  int nsx, nsy, rseg, ntasks;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bulk_store(float* gdst, const float* ssrc, unsigned bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct Task { int n, x0, y0, y1; };
+__device__ __forceinline__ Task task_decode(int t, const Params& p) {
+  Task k;
+  const int per_img = p.nsx * p.nsy;
+  k.n = t / per_img;
+  const int r = t - k.n * per_img;
+  const int sy = r / p.nsx;
+  k.x0 = (r - sy * p.nsx) * SW;
+  k.y0 = sy * p.rseg;
+  k.y1 = min(k.y0 + p.rseg, p.h);
+  return k;
+}
+
+// fixed-point intensity for histogram B: rne(I * B * 2^24); I is already clamped to [-2, 3] (NaN -> -2: no vote)
+__device__ __forceinline__ int to_fix(float v, float scale) { return __float2int_rn(v * scale); }
+
+// G_j of a histogram, j = 0..B: clamp(T - (j - 0.5) * 2^24, 0, 2^24)   (bin b = j + 1 has vote G_j - G_{j+1})
+__device__ __forceinline__ int gval(int t, int j) { return __viaddmin_s32_relu(t, (1 << 23) - j * (1 << 24), CAPV); }
+
+// ------------------------------------------------------------------------------------------ producers
+// HALF 0: histograms B = 4 (5 G) and B = 8 (9 G) of one (column, colour); HALF 1: B = 16 (17 G).
+template <int HALF>
+__device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, int* __restrict__ ring, uint64_t* bars,
+                                         int ptid) {
+  constexpr int NG = HALF ? 17 : 14;
+  const int rem = ptid - HALF * (NPROD / 2);
+  const bool act = rem < NPT;
+  const int colour = act ? rem / CW : 0;
+  const int col = act ? rem - colour * CW : 0;
+  const int lane = ptid & 31;
+  int* myring = ring + (HALF ? 2 * NPT : 0) + (act ? rem : 0);   // HALF 0: T4 at +0, T8 at +NPT
+  int S[NG];
+  unsigned q = 0;
+  for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
+    const Task k = task_decode(t, p);
+    const int gx = k.x0 - HL + col;
+    const bool xok = act && gx >= 0 && gx < p.w;
+    const float* src = p.img + ((long long)k.n * p.h * p.w + gx) * 3 + colour;
+    const long long rstride = (long long)p.w * 3;
+    auto load = [&](int r) -> float {
+      float v = -2.0f;
+      if (xok && r < p.h) v = __ldg(src + r * rstride);        // r >= 0 always
+      return fminf(fmaxf(v, -2.0f), 3.0f);                     // NaN -> -2 (votes 0, like tf.where on a NaN compare)
+    };
+#pragma unroll
+    for (int j = 0; j < NG; ++j) S[j] = 0;
+    if (act) {
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        myring[s * RING_P] = T_OUT;
+        if (!HALF) myring[s * RING_P + NPT] = T_OUT;
+      }
+    }
+    // warm-up: rows y0-7 .. y0+7 enter, nothing leaves, nothing is emitted
+    int r = max(k.y0 - HL, 0);
+    float nxt = load(r);
+    for (; r <= k.y0 + HL; ++r) {
+      const float cur = nxt;
+      nxt = load(r + 1);
+      int* rs = myring + (r & 15) * RING_P;
+      if (HALF) {
+        const int tn = to_fix(cur, 268435456.0f);
+        if (act) rs[0] = tn;
+#pragma unroll
+        for (int j = 0; j < 17; ++j) S[j] += gval(tn, j);
+      } else {
+        const int ta = to_fix(cur, 67108864.0f), tb = to_fix(cur, 134217728.0f);
+        if (act) { rs[0] = ta; rs[NPT] = tb; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) S[j] += gval(ta, j);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) S[5 + j] += gval(tb, j);
+      }
+    }
+    // steady state: row y+8 enters, row y-8 leaves, row y is emitted
+    for (int y = k.y0; y < k.y1; ++y, ++q) {
+      r = y + HR;
+      const float cur = nxt;
+      nxt = load(r + 1);
+      int* rs = myring + (r & 15) * RING_P;
+      if (HALF) {
+        const int tn = to_fix(cur, 268435456.0f);
+        const int to = rs[0];
+        if (act) rs[0] = tn;
+#pragma unroll
+        for (int j = 0; j < 17; ++j) S[j] += gval(tn, j) - gval(to, j);
+      } else {
+        const int ta = to_fix(cur, 67108864.0f), tb = to_fix(cur, 134217728.0f);
+        const int oa = rs[0], ob = rs[NPT];
+        if (act) { rs[0] = ta; rs[NPT] = tb; }
+#pragma unroll
+        for (int j = 0; j < 5; ++j) S[j] += gval(ta, j) - gval(oa, j);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) S[5 + j] += gval(tb, j) - gval(ob, j);
+      }
+      const unsigned s = q % NST, ph = (q / NST) & 1u;
+      mbar_wait(bars + NST + s, ph ^ 1u);                      // consumers have read the previous row in this stage
+      if (act) {
+        // column vote sums (16 rows): <= 2^28; capped at 2^28 - 1 so that 16 of them never reach 2^32 (the cap moves a
+        // window that is all exact 1.0 votes by 2^-28 relative, below the fp32 rounding of the result)
+        int* dst = sS + s * STAGE_INTS + colour * VP + col;
+        if (HALF) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dst[(36 + 3 * i) * VP] = __viaddmin_s32(S[i], -S[i + 1], (1 << 28) - 1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[(3 * i) * VP] = __viaddmin_s32(S[i], -S[i + 1], (1 << 28) - 1);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[(12 + 3 * i) * VP] = __viaddmin_s32(S[5 + i], -S[6 + i], (1 << 28) - 1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + s);                    // release: this warp's column sums are in the stage
+    }
+  }
+}
+
+// Sobel of one (pixel, colour) at image row y, column gx: same tap order as k_frontend_strip (frontend.cu)
+__device__ __forceinline__ void sobel_at(const float* __restrict__ q, int y, int gx, int h, int w, float& v, float& dy,
+                                         float& dx) {
+  const long long oym = (long long)(reflect1(y - 1, h) - y) * w * 3;
+  const long long oyp = (long long)(reflect1(y + 1, h) - y) * w * 3;
+  const int oxm = (reflect1(gx - 1, w) - gx) * 3;
+  const int oxp = (reflect1(gx + 1, w) - gx) * 3;
+  const float p00 = __ldg(q + oym + oxm), p01 = __ldg(q + oym), p02 = __ldg(q + oym + oxp);
+  const float p10 = __ldg(q + oxm), p12 = __ldg(q + oxp);
+  const float p20 = __ldg(q + oyp + oxm), p21 = __ldg(q + oyp), p22 = __ldg(q + oyp + oxp);
+  v = __ldg(q);
+  dy = -p00;
+  dy = __fadd_rn(dy, -2.0f * p01);
+  dy = __fsub_rn(dy, p02);
+  dy = __fadd_rn(dy, p20);
+  dy = __fadd_rn(dy, 2.0f * p21);
+  dy = __fadd_rn(dy, p22);
+  dx = -p00;
+  dx = __fadd_rn(dx, p02);
+  dx = __fadd_rn(dx, -2.0f * p10);
+  dx = __fadd_rn(dx, 2.0f * p12);
+  dx = __fsub_rn(dx, p20);
+  dx = __fadd_rn(dx, p22);
+}
+
+// ------------------------------------------------------------------------------------------ consumers
+template <bool FULL>
+__device__ __forceinline__ void consumer(const Params& p, const int* __restrict__ sS, float* __restrict__ sStg,
+                                         float* __restrict__ sRow, uint64_t* bars, int ctid) {
+  constexpr int CO = Cfg<FULL>::CO, CH0 = Cfg<FULL>::CH0;
+  const int lane = ctid & 31;
+  const int cw = ctid >> 5;
+  const int g = cw / 6;                    // row group: emitted rows with (q & 1) == g
+  const int sub = cw - 6 * g;
+  const int seg = sub & 1;                 // half strip: output columns 32*seg .. +31
+  const int ch = (sub >> 1) * 32 + lane;   // this lane's histogram channel
+  const bool actv = ch < NH;
+  const int chr = actv ? ch : NH - 1;
+  const int gtid = ctid - g * GROUP;
+  const bool elected = (gtid == 0);
+  float* stg = sStg + g * (SW * CO);
+  float* rowsc = sRow + g * SW;
+  float* my = stg + (seg * 32) * CO + CH0 + ch;
+  unsigned q = 0;
+  for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
+    const Task k = task_decode(t, p);
+    const bool xedge = (k.x0 == 0) || (k.x0 + SW + HR > p.w);
+    const int vw = min(SW, p.w - k.x0);
+    float* orow = p.out + (((long long)k.n * p.h + k.y0) * p.w + k.x0) * CO;
+    for (int y = k.y0; y < k.y1; ++y, ++q, orow += (long long)p.w * CO) {
+      if ((q & 1u) != (unsigned)g) continue;
+      float fv = 0.f, fdy = 0.f, fdx = 0.f;
+      int fpx = -1, fc = 0;
+      if (FULL) {                          // img + Sobel of one (pixel, colour) of this row, loads issued early
+        const int item = sub * 32 + lane;  // 0..191 = 64 pixels x 3 colours
+        const int px = item / 3;
+        fc = item - px * 3;
+        if (k.x0 + px < p.w) {
+          fpx = px;
+          sobel_at(p.img + (((long long)k.n * p.h + y) * p.w + k.x0 + px) * 3 + fc, y, k.x0 + px, p.h, p.w, fv, fdy, fdx);
+        }
+      }
+      const int ny = min(y + HR, p.h - 1) - max(y - HL, 0) + 1;
+      const unsigned s = q % NST, ph = (q / NST) & 1u;
+      mbar_wait(bars + s, ph);             // producers filled this stage
+      const int4* vl = reinterpret_cast<const int4*>(sS + s * STAGE_INTS + chr * VP + seg * 32);
+      unsigned v[48];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const int4 x4 = vl[i];
+        v[4 * i + 0] = (unsigned)x4.x; v[4 * i + 1] = (unsigned)x4.y;
+        v[4 * i + 2] = (unsigned)x4.z; v[4 * i + 3] = (unsigned)x4.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + NST + s);              // this warp holds its 47 column sums in registers
+      if (elected) bulk_wait_read();       // the group's previous row has left the staging buffer
+      if (xedge && gtid < SW) {            // per-column scale of a strip that touches the left / right image border
+        const int gx = k.x0 + gtid;
+        const int nx = max(min(gx + HR, p.w - 1) - max(gx - HL, 0) + 1, 1);
+        rowsc[gtid] = __fdiv_rn(1.0f, (float)(ny * nx)) * (1.0f / 16777216.0f);
+      }
+      named_bar_sync(1 + g, GROUP);        // staging buffer free, scales visible
+      const float sc = __fdiv_rn(1.0f, (float)(ny * PK)) * (1.0f / 16777216.0f);
+      unsigned H = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) H += v[i];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (j > 0) H += v[j + 15] - v[j - 1];
+        const float f = __uint2float_rn(H) * (xedge ? rowsc[seg * 32 + j] : sc);
+        if (actv) my[j * CO] = f;
+      }
+      if (FULL && fpx >= 0) {
+        float* o = stg + fpx * CO;
+        o[fc] = fv;
+        o[3 + fc * 2] = fdy;
+        o[4 + fc * 2] = fdx;
+      }
+      fence_async_smem();                  // staging writes -> visible to the bulk-copy (async) proxy
+      named_bar_sync(1 + g, GROUP);        // the whole row is staged
+      if (elected) {
+        bulk_store(orow, stg, (unsigned)(vw * CO * 4));
+        bulk_commit();
+      }
+    }
+  }
+  if (elected) bulk_wait_all();
+}
+
+template <bool FULL>
+__global__ void __launch_bounds__(THREADS, 1) k_pool_slide(const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* sStg = reinterpret_cast<float*>(smem_raw);                       // bulk-copy source: 16-byte aligned
+  int* sS = reinterpret_cast<int*>(sStg + 2 * SW * Cfg<FULL>::CO);
+  int* ring = sS + NST * STAGE_INTS;
+  float* sRow = reinterpret_cast<float*>(ring + 16 * RING_P);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 2 * SW);            // full[NST], empty[NST]
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(bars + s, NPW);
+      mbar_init(bars + NST + s, NCW / 2);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < NPROD / 2) producer<0>(p, sS, ring, bars, tid);
+  else if (tid < NPROD) producer<1>(p, sS, ring, bars, tid);
+  else consumer<FULL>(p, sS, sStg, sRow, bars, tid - NPROD);
+}
+
+template <bool FULL>
+static int launch_t(const Params& p, int sms, cudaStream_t st) {
+  SHDR_CUDA(cudaFuncSetAttribute(k_pool_slide<FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)Cfg<FULL>::SMEM));
+  const int grid = p.ntasks < sms ? p.ntasks : sms;
+  k_pool_slide<FULL><<<grid, THREADS, Cfg<FULL>::SMEM, st>>>(p);
+  SHDR_LAUNCH_CHECK("k_pool_slide");
+  return SHDR_OK;
+}
+
+}  // namespace sl
+
+// true when the sliding-window kernel can run this request: the {4, 8, 16} histograms into a dense 84-channel tensor,
+// or (full93) into channels 9..92 of the 93-channel front-end tensor together with img + Sobel in channels 0..8.
+// The per-row bulk copies need 16-byte aligned chunks: always true for 84 channels (336 B per pixel); for 93 channels
+// (372 B per pixel) the image width must be a multiple of 4.
+bool pool_slide_supported(const float* out, int w, const int* bins, int nbins, bool full93) {
+  if (nbins != 3 || bins[0] != 4 || bins[1] != 8 || bins[2] != 16) return false;
+  if (!aligned16(out)) return false;
+  return full93 ? (w % 4) == 0 : true;
+}
+
+int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool full93, int dev, cudaStream_t st) {
+  sl::Params p;
+  p.img = img; p.out = out; p.n = n; p.h = h; p.w = w;
+  p.nsx = (w + sl::SW - 1) / sl::SW;
+  const int sms = sm_count(dev);
+  // row segments: every task pays a warm-up of 15 rows (about 6 rows' worth of work); pick the split that minimises
+  // waves x (rows per task + warm-up)
+  long long best_cost = -1;
+  int best_nsy = 1;
+  for (int nsy = 1; nsy <= (h + 31) / 32; ++nsy) {
+    const int rseg = (h + nsy - 1) / nsy;
+    const long long tasks = (long long)n * p.nsx * ((h + rseg - 1) / rseg);
+    const long long waves = (tasks + sms - 1) / sms;
+    const long long cost = waves * (rseg + 6);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_nsy = nsy; }
+  }
+  p.rseg = (h + best_nsy - 1) / best_nsy;
+  p.nsy = (h + p.rseg - 1) / p.rseg;
+  const long long total = (long long)n * p.nsx * p.nsy;
+  SHDR_REQUIRE(total > 0 && total < 0x7fffffffLL, "pool_slide: %lld tasks out of range", total);
+  p.ntasks = (int)total;
+  return full93 ? sl::launch_t<true>(p, sms, st) : sl::launch_t<false>(p, sms, st);
+}
+
+}  // namespace shdr

@@ -24,7 +24,6 @@
 //     to HBM with TMA bulk-tensor stores (cp.async.bulk.tensor.4d, SASS UTMASTG): a 4-D tensor map over
 //     (float, row, pixel pair, image) addresses whole sectors and clips at the image border by itself.
 #include <cuda.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -64,7 +63,6 @@ struct Params {
   int C;                     // output channels per pixel (multiple of 4)
   int n, h, w;
   int tiles_x, tiles_y, tiles_total;
-  int dbg;                   // profiling experiments only (SHDR_POOL_DBG): 0 = normal, 1 = no global stores
 };
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
@@ -427,7 +425,7 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
         mbar_arrive(bars + NSTAGE + s);     // this thread is done reading sV[s]
         fence_async_smem();                 // make this thread's staging writes visible to the async (TMA) proxy
         __syncwarp();                       // the warp's part of the unit is staged (and its parked sHead is visible)
-        if (lane == 0 && prm.dbg != 1) {
+        if (lane == 0) {
           if (!EO) {
             tma_store4(&tmap, wst, u * UC, ty, tx, tc.n);                                   // [32 px][4 rows][8 ch]
           } else {
@@ -524,7 +522,6 @@ int launch_hist_pooled_ws(const float* img, float* out, int n, int h, int w, con
   const long long total = (long long)n * p.tiles_x * p.tiles_y;
   SHDR_REQUIRE(total > 0 && total < 0x7fffffffLL, "hist_pooled_ws: %lld tiles out of range", total);
   p.tiles_total = (int)total;
-  { const char* e = getenv("SHDR_POOL_DBG"); p.dbg = e ? atoi(e) : 0; }
   const int sms = sm_count(dev);
   switch (C) {
     case 84: return ws::launch_t<84, true>(img, out, p, sms, st);    // B = 4, 8, 16
