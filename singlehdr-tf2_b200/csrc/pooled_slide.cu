@@ -52,11 +52,12 @@ constexpr int NPROD = NPW * 32, NCONS = NCW * 32, THREADS = NPROD + NCONS;
 constexpr int GROUP = NCONS / 2;             // threads of one consumer row group
 constexpr int CAPV = 1 << 24;                // vote 1.0
 constexpr int T_OUT = -(1 << 30);            // "no pixel": every G is 0
+constexpr int TAB = 17 * 17 + 3;             // 1 / (ny * nx * 2^24) for ny, nx = 0..16 (+ pad)
 
 template <bool FULL> struct Cfg {
   static constexpr int CO = FULL ? SHDR_FRONTEND_CH : SHDR_HIST_CH;   // floats per output pixel
   static constexpr int CH0 = FULL ? 9 : 0;                            // first histogram channel
-  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P + 2 * SW * CO + 2 * SW) * 4 + 2 * NST * 8;
+  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P + 2 * SW * CO + 2 * SW + TAB) * 4 + 2 * NST * 8;
 };
 
 struct Params {
@@ -194,17 +195,16 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
       const unsigned s = q % NST, ph = (q / NST) & 1u;
       mbar_wait(bars + NST + s, ph ^ 1u);                      // consumers have read the previous row in this stage
       if (act) {
-        // column vote sums (16 rows): <= 2^28; capped at 2^28 - 1 so that 16 of them never reach 2^32 (the cap moves a
-        // window that is all exact 1.0 votes by 2^-28 relative, below the fp32 rounding of the result)
+        // column vote sums over the 16 rows: S_b - S_{b+1} <= 2^28
         int* dst = sS + s * STAGE_INTS + colour * VP + col;
         if (HALF) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dst[(36 + 3 * i) * VP] = __viaddmin_s32(S[i], -S[i + 1], (1 << 28) - 1);
+          for (int i = 0; i < 16; ++i) dst[(36 + 3 * i) * VP] = S[i] - S[i + 1];
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[(3 * i) * VP] = __viaddmin_s32(S[i], -S[i + 1], (1 << 28) - 1);
+          for (int i = 0; i < 4; ++i) dst[(3 * i) * VP] = S[i] - S[i + 1];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[(12 + 3 * i) * VP] = __viaddmin_s32(S[5 + i], -S[6 + i], (1 << 28) - 1);
+          for (int i = 0; i < 8; ++i) dst[(12 + 3 * i) * VP] = S[5 + i] - S[6 + i];
         }
       }
       __syncwarp();
@@ -239,9 +239,51 @@ __device__ __forceinline__ void sobel_at(const float* __restrict__ q, int y, int
 }
 
 // ------------------------------------------------------------------------------------------ consumers
+// One output row of one lane: 47 column sums of its channel -> 32 window sums -> fp32 -> scaled -> staging.
+// XEDGE: the strip touches the left / right image border, so the in-bounds count varies along the row (scale per
+// column from rowsc[]); otherwise one scale for the whole row.
+template <bool XEDGE, int CO>
+__device__ __forceinline__ void consume_row(const int4* __restrict__ vl, float* __restrict__ my, float sc,
+                                            const float* __restrict__ rowsc, bool actv, uint64_t* empty_bar, int lane) {
+  unsigned v[48];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const int4 x4 = vl[i];
+    v[4 * i + 0] = (unsigned)x4.x; v[4 * i + 1] = (unsigned)x4.y;
+    v[4 * i + 2] = (unsigned)x4.z; v[4 * i + 3] = (unsigned)x4.w;
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);                 // this warp holds its 47 column sums in registers
+  // A column sum can be 2^28 (sixteen exact 1.0 votes) and sixteen of those would wrap to 0.  Every window of 16
+  // consecutive columns holds exactly one column whose strip index is a multiple of 16: capping those at 2^28 - 1
+  // keeps every window sum below 2^32 and moves an all-ones window by 2^-32 relative (below the fp32 rounding).
+  v[0] = min(v[0], (1u << 28) - 1); v[16] = min(v[16], (1u << 28) - 1); v[32] = min(v[32], (1u << 28) - 1);
+  // two independent chains (outputs 0..15 and 16..31) halve the dependent-add latency
+  unsigned h0 = 0, h1 = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { h0 += v[i]; h1 += v[16 + i]; }
+  unsigned H[32];
+  H[0] = h0; H[16] = h1;
+#pragma unroll
+  for (int j = 1; j < 16; ++j) {
+    H[j] = H[j - 1] + v[j + 15] - v[j - 1];
+    H[16 + j] = H[16 + j - 1] + v[16 + j + 15] - v[16 + j - 1];
+  }
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint2float_rn(H[j]);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] *= XEDGE ? rowsc[j] : sc;
+  if (actv) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) my[j * CO] = f[j];
+  }
+}
+
 template <bool FULL>
 __device__ __forceinline__ void consumer(const Params& p, const int* __restrict__ sS, float* __restrict__ sStg,
-                                         float* __restrict__ sRow, uint64_t* bars, int ctid) {
+                                         float* __restrict__ sRow, const float* __restrict__ sTab, uint64_t* bars,
+                                         int ctid) {
   constexpr int CO = Cfg<FULL>::CO, CH0 = Cfg<FULL>::CH0;
   const int lane = ctid & 31;
   const int cw = ctid >> 5;
@@ -256,12 +298,18 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
   float* stg = sStg + g * (SW * CO);
   float* rowsc = sRow + g * SW;
   float* my = stg + (seg * 32) * CO + CH0 + ch;
+  const int* myS = sS + chr * VP + seg * 32;
   unsigned q = 0;
   for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
     const Task k = task_decode(t, p);
     const bool xedge = (k.x0 == 0) || (k.x0 + SW + HR > p.w);
     const int vw = min(SW, p.w - k.x0);
     float* orow = p.out + (((long long)k.n * p.h + k.y0) * p.w + k.x0) * CO;
+    int nx = PK;                           // in-bounds columns of this thread's scale-table column (gtid < 64)
+    if (gtid < SW) {
+      const int gx = k.x0 + gtid;
+      nx = min(max(min(gx + HR, p.w - 1) - max(gx - HL, 0) + 1, 0), PK);
+    }
     for (int y = k.y0; y < k.y1; ++y, ++q, orow += (long long)p.w * CO) {
       if ((q & 1u) != (unsigned)g) continue;
       float fv = 0.f, fdy = 0.f, fdx = 0.f;
@@ -277,34 +325,13 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
       }
       const int ny = min(y + HR, p.h - 1) - max(y - HL, 0) + 1;
       const unsigned s = q % NST, ph = (q / NST) & 1u;
-      mbar_wait(bars + s, ph);             // producers filled this stage
-      const int4* vl = reinterpret_cast<const int4*>(sS + s * STAGE_INTS + chr * VP + seg * 32);
-      unsigned v[48];
-#pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const int4 x4 = vl[i];
-        v[4 * i + 0] = (unsigned)x4.x; v[4 * i + 1] = (unsigned)x4.y;
-        v[4 * i + 2] = (unsigned)x4.z; v[4 * i + 3] = (unsigned)x4.w;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bars + NST + s);              // this warp holds its 47 column sums in registers
       if (elected) bulk_wait_read();       // the group's previous row has left the staging buffer
-      if (xedge && gtid < SW) {            // per-column scale of a strip that touches the left / right image border
-        const int gx = k.x0 + gtid;
-        const int nx = max(min(gx + HR, p.w - 1) - max(gx - HL, 0) + 1, 1);
-        rowsc[gtid] = __fdiv_rn(1.0f, (float)(ny * nx)) * (1.0f / 16777216.0f);
-      }
+      if (xedge && gtid < SW) rowsc[gtid] = sTab[ny * 17 + nx];
       named_bar_sync(1 + g, GROUP);        // staging buffer free, scales visible
-      const float sc = __fdiv_rn(1.0f, (float)(ny * PK)) * (1.0f / 16777216.0f);
-      unsigned H = 0;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) H += v[i];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (j > 0) H += v[j + 15] - v[j - 1];
-        const float f = __uint2float_rn(H) * (xedge ? rowsc[seg * 32 + j] : sc);
-        if (actv) my[j * CO] = f;
-      }
+      mbar_wait(bars + s, ph);             // producers filled this stage
+      const int4* vl = reinterpret_cast<const int4*>(myS + s * STAGE_INTS);
+      if (xedge) consume_row<true, CO>(vl, my, 0.f, rowsc + seg * 32, actv, bars + NST + s, lane);
+      else consume_row<false, CO>(vl, my, sTab[ny * 17 + PK], nullptr, actv, bars + NST + s, lane);
       if (FULL && fpx >= 0) {
         float* o = stg + fpx * CO;
         o[fc] = fv;
@@ -329,8 +356,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_pool_slide(const __grid_constant
   int* sS = reinterpret_cast<int*>(sStg + 2 * SW * Cfg<FULL>::CO);
   int* ring = sS + NST * STAGE_INTS;
   float* sRow = reinterpret_cast<float*>(ring + 16 * RING_P);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sRow + 2 * SW);            // full[NST], empty[NST]
+  float* sTab = sRow + 2 * SW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sTab + TAB);               // full[NST], empty[NST]
   const int tid = threadIdx.x;
+  if (tid < 17 * 17) {                     // 1 / (in-bounds count * 2^24): 2^-24 undoes the fixed-point vote scale
+    const int cnt = (tid / 17) * (tid % 17);
+    sTab[tid] = cnt ? __fdiv_rn(1.0f, (float)cnt) * (1.0f / 16777216.0f) : 0.0f;
+  }
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(bars + s, NPW);
@@ -341,7 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_pool_slide(const __grid_constant
   __syncthreads();
   if (tid < NPROD / 2) producer<0>(p, sS, ring, bars, tid);
   else if (tid < NPROD) producer<1>(p, sS, ring, bars, tid);
-  else consumer<FULL>(p, sS, sStg, sRow, bars, tid - NPROD);
+  else consumer<FULL>(p, sS, sStg, sRow, sTab, bars, tid - NPROD);
 }
 
 template <bool FULL>
