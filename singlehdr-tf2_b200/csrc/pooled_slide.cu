@@ -136,10 +136,11 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
     const bool xok = act && gx >= 0 && gx < p.w;
     const float* src = p.img + ((long long)k.n * p.h * p.w + gx) * 3 + colour;
     const long long rstride = (long long)p.w * 3;
-    auto load = [&](int r) -> float {
-      float v = -2.0f;
-      if (xok && r < p.h) v = __ldg(src + r * rstride);        // r >= 0 always
-      return fminf(fmaxf(v, -2.0f), 3.0f);                     // NaN -> -2 (votes 0, like tf.where on a NaN compare)
+    auto load = [&](int r) -> float {                          // r >= 0 always; out of the image: no vote
+      return (xok && r < p.h) ? __ldg(src + r * rstride) : -2.0f;
+    };
+    auto clampv = [](float v) -> float {                       // NaN -> -2 (votes 0, like tf.where on a NaN compare)
+      return fminf(fmaxf(v, -2.0f), 3.0f);
     };
 #pragma unroll
     for (int j = 0; j < NG; ++j) S[j] = 0;
@@ -154,7 +155,7 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
     int r = max(k.y0 - HL, 0);
     float nxt = load(r);
     for (; r <= k.y0 + HL; ++r) {
-      const float cur = nxt;
+      const float cur = clampv(nxt);
       nxt = load(r + 1);
       int* rs = myring + (r & 15) * RING_P;
       if (HALF) {
@@ -174,7 +175,7 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
     // steady state: row y+8 enters, row y-8 leaves, row y is emitted
     for (int y = k.y0; y < k.y1; ++y, ++q) {
       r = y + HR;
-      const float cur = nxt;
+      const float cur = clampv(nxt);
       nxt = load(r + 1);
       int* rs = myring + (r & 15) * RING_P;
       if (HALF) {
@@ -239,12 +240,12 @@ __device__ __forceinline__ void sobel_at(const float* __restrict__ q, int y, int
 }
 
 // ------------------------------------------------------------------------------------------ consumers
-// One output row of one lane: 47 column sums of its channel -> 32 window sums -> fp32 -> scaled -> staging.
-// XEDGE: the strip touches the left / right image border, so the in-bounds count varies along the row (scale per
-// column from rowsc[]); otherwise one scale for the whole row.
-template <bool XEDGE, int CO>
-__device__ __forceinline__ void consume_row(const int4* __restrict__ vl, float* __restrict__ my, float sc,
-                                            const float* __restrict__ rowsc, bool actv, uint64_t* empty_bar, int lane) {
+// One output row of one lane, part 1: 47 column sums of its channel -> 32 window sums -> fp32 (-> scaled when one
+// scale serves the whole row).  Runs BEFORE the group's staging buffer is known to be free, so it overlaps the bulk
+// store of the group's previous row.
+template <bool SCALE>
+__device__ __forceinline__ void window_sums(const int4* __restrict__ vl, float (&f)[32], float sc, uint64_t* empty_bar,
+                                            int lane) {
   unsigned v[48];
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
@@ -269,14 +270,11 @@ __device__ __forceinline__ void consume_row(const int4* __restrict__ vl, float* 
     H[j] = H[j - 1] + v[j + 15] - v[j - 1];
     H[16 + j] = H[16 + j - 1] + v[16 + j + 15] - v[16 + j - 1];
   }
-  float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint2float_rn(H[j]);
+  if (SCALE) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] *= XEDGE ? rowsc[j] : sc;
-  if (actv) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) my[j * CO] = f[j];
+    for (int j = 0; j < 32; ++j) f[j] *= sc;
   }
 }
 
@@ -325,13 +323,23 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
       }
       const int ny = min(y + HR, p.h - 1) - max(y - HL, 0) + 1;
       const unsigned s = q % NST, ph = (q / NST) & 1u;
+      mbar_wait(bars + s, ph);             // producers filled this stage
+      const int4* vl = reinterpret_cast<const int4*>(myS + s * STAGE_INTS);
+      float f[32];
+      if (xedge) window_sums<false>(vl, f, 0.f, bars + NST + s, lane);
+      else window_sums<true>(vl, f, sTab[ny * 17 + PK], bars + NST + s, lane);
       if (elected) bulk_wait_read();       // the group's previous row has left the staging buffer
       if (xedge && gtid < SW) rowsc[gtid] = sTab[ny * 17 + nx];
       named_bar_sync(1 + g, GROUP);        // staging buffer free, scales visible
-      mbar_wait(bars + s, ph);             // producers filled this stage
-      const int4* vl = reinterpret_cast<const int4*>(myS + s * STAGE_INTS);
-      if (xedge) consume_row<true, CO>(vl, my, 0.f, rowsc + seg * 32, actv, bars + NST + s, lane);
-      else consume_row<false, CO>(vl, my, sTab[ny * 17 + PK], nullptr, actv, bars + NST + s, lane);
+      if (xedge) {                         // the in-bounds count varies along the row: one scale per column
+        const float* rs = rowsc + seg * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] *= rs[j];
+      }
+      if (actv) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) my[j * CO] = f[j];
+      }
       if (FULL && fpx >= 0) {
         float* o = stg + fpx * CO;
         o[fc] = fv;
