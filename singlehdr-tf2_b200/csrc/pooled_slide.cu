@@ -52,6 +52,7 @@ constexpr int NPROD = NPW * 32, NCONS = NCW * 32, THREADS = NPROD + NCONS;
 constexpr int GROUP = NCONS / 2;             // threads of one consumer row group
 constexpr int CAPV = 1 << 24;                // vote 1.0
 constexpr int T_OUT = -(1 << 30);            // "no pixel": every G is 0
+constexpr int PFD = 8;                       // rows of L2 prefetch distance for the input
 constexpr int TAB = 17 * 17 + 3;             // 1 / (ny * nx * 2^24) for ny, nx = 0..16 (+ pad)
 
 template <bool FULL> struct Cfg {
@@ -139,6 +140,12 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
     auto load = [&](int r) -> float {                          // r >= 0 always; out of the image: no vote
       return (xok && r < p.h) ? __ldg(src + r * rstride) : -2.0f;
     };
+    // The register prefetch (one row ahead) only covers an L2 hit; under the write stream a DRAM read takes longer
+    // than a row, so every eighth column also pulls the row PFD rows ahead into L2 (a row of the strip is 948 B).
+    const bool pf = xok && colour == 0 && ((col & 7) == 0 || col == CW - 1);
+    auto prefetch = [&](int r) {
+      if (pf && r < p.h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * rstride));
+    };
     auto clampv = [](float v) -> float {                       // NaN -> -2 (votes 0, like tf.where on a NaN compare)
       return fminf(fmaxf(v, -2.0f), 3.0f);
     };
@@ -153,10 +160,13 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
     }
     // warm-up: rows y0-7 .. y0+7 enter, nothing leaves, nothing is emitted
     int r = max(k.y0 - HL, 0);
+#pragma unroll 1
+    for (int i = 1; i < PFD; ++i) prefetch(r + i);
     float nxt = load(r);
     for (; r <= k.y0 + HL; ++r) {
       const float cur = clampv(nxt);
       nxt = load(r + 1);
+      prefetch(r + PFD);
       int* rs = myring + (r & 15) * RING_P;
       if (HALF) {
         const int tn = to_fix(cur, 268435456.0f);
@@ -177,6 +187,7 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
       r = y + HR;
       const float cur = clampv(nxt);
       nxt = load(r + 1);
+      prefetch(r + PFD);
       int* rs = myring + (r & 15) * RING_P;
       if (HALF) {
         const int tn = to_fix(cur, 268435456.0f);
