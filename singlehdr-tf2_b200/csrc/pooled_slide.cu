@@ -43,7 +43,7 @@ constexpr int SW = 64;                       // output columns per strip
 constexpr int CW = SW + HL + HR;             // 79 input columns
 constexpr int NH = 84;                       // histogram channels: 3 * (4 + 8 + 16)
 constexpr int VP = 84;                       // ints per channel line of a stage (79 + pad; 84 = 20 mod 32)
-constexpr int NST = 4;                       // column-sum stages
+constexpr int NST = 3;                       // column-sum stages
 constexpr int STAGE_INTS = NH * VP;          // 7056 ints = 28 KB
 constexpr int NPT = 3 * CW;                  // 237 (column, colour) pairs
 constexpr int RING_P = 3 * NPT + 1;          // ints per ring row: T4 | T8 | T16
@@ -58,7 +58,7 @@ constexpr int TAB = 17 * 17 + 3;             // 1 / (ny * nx * 2^24) for ny, nx 
 template <bool FULL> struct Cfg {
   static constexpr int CO = FULL ? SHDR_FRONTEND_CH : SHDR_HIST_CH;   // floats per output pixel
   static constexpr int CH0 = FULL ? 9 : 0;                            // first histogram channel
-  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P + 2 * SW * CO + 2 * SW + TAB) * 4 + 2 * NST * 8;
+  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P + 4 * SW * CO + 2 * SW + TAB) * 4 + 2 * NST * 8;
 };
 
 struct Params {
@@ -129,26 +129,19 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
   const int col = act ? rem - colour * CW : 0;
   const int lane = ptid & 31;
   int* myring = ring + (HALF ? 2 * NPT : 0) + (act ? rem : 0);   // HALF 0: T4 at +0, T8 at +NPT
+  int* mydst = sS + (colour + (HALF ? 36 : 0)) * VP + col;       // this thread's first channel line, stage 0
+  const int h = p.h, rs3 = p.w * 3;
+  const int pfoff = (PFD - 1) * rs3;
   int S[NG];
-  unsigned q = 0;
+  unsigned s = 0, ph = 1;                  // stage of the next emitted row; parity of its "empty" wait (first use passes)
   for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
     const Task k = task_decode(t, p);
     const int gx = k.x0 - HL + col;
     const bool xok = act && gx >= 0 && gx < p.w;
-    const float* src = p.img + ((long long)k.n * p.h * p.w + gx) * 3 + colour;
-    const long long rstride = (long long)p.w * 3;
-    auto load = [&](int r) -> float {                          // r >= 0 always; out of the image: no vote
-      return (xok && r < p.h) ? __ldg(src + r * rstride) : -2.0f;
-    };
+    const float* src = p.img + ((long long)k.n * h * p.w + gx) * 3 + colour;
     // The register prefetch (one row ahead) only covers an L2 hit; under the write stream a DRAM read takes longer
     // than a row, so every eighth column also pulls the row PFD rows ahead into L2 (a row of the strip is 948 B).
     const bool pf = xok && colour == 0 && ((col & 7) == 0 || col == CW - 1);
-    auto prefetch = [&](int r) {
-      if (pf && r < p.h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + r * rstride));
-    };
-    auto clampv = [](float v) -> float {                       // NaN -> -2 (votes 0, like tf.where on a NaN compare)
-      return fminf(fmaxf(v, -2.0f), 3.0f);
-    };
 #pragma unroll
     for (int j = 0; j < NG; ++j) S[j] = 0;
     if (act) {
@@ -158,15 +151,24 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
         if (!HALF) myring[s * RING_P + NPT] = T_OUT;
       }
     }
-    // warm-up: rows y0-7 .. y0+7 enter, nothing leaves, nothing is emitted
-    int r = max(k.y0 - HL, 0);
+    int r = max(k.y0 - HL, 0);             // the row that enters next; rows are addressed as src[off], off = row * rs3
+    int off = r * rs3;
 #pragma unroll 1
-    for (int i = 1; i < PFD; ++i) prefetch(r + i);
-    float nxt = load(r);
+    for (int i = 1; i < PFD; ++i)
+      if (pf && r + i < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + i * rs3));
+    float nxt = (xok && r < h) ? __ldg(src + off) : -2.0f;     // out of the image: no vote
+    // one row step: clamp the row loaded during the previous step (NaN -> -2: votes 0, like tf.where on a NaN
+    // compare), start the load of the next row and the L2 prefetch PFD rows ahead
+    auto advance = [&]() -> float {
+      const float cur = fminf(fmaxf(nxt, -2.0f), 3.0f);
+      off += rs3;
+      nxt = (xok && r + 1 < h) ? __ldg(src + off) : -2.0f;
+      if (pf && r + PFD < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + pfoff));
+      return cur;
+    };
+    // warm-up: rows y0-7 .. y0+7 enter, nothing leaves, nothing is emitted
     for (; r <= k.y0 + HL; ++r) {
-      const float cur = clampv(nxt);
-      nxt = load(r + 1);
-      prefetch(r + PFD);
+      const float cur = advance();
       int* rs = myring + (r & 15) * RING_P;
       if (HALF) {
         const int tn = to_fix(cur, 268435456.0f);
@@ -182,12 +184,10 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
         for (int j = 0; j < 9; ++j) S[5 + j] += gval(tb, j);
       }
     }
-    // steady state: row y+8 enters, row y-8 leaves, row y is emitted
-    for (int y = k.y0; y < k.y1; ++y, ++q) {
-      r = y + HR;
-      const float cur = clampv(nxt);
-      nxt = load(r + 1);
-      prefetch(r + PFD);
+    // steady state: row r = y+8 enters, row y-8 leaves, row y is emitted
+    const int rend = k.y1 + HR;
+    for (; r < rend; ++r) {
+      const float cur = advance();
       int* rs = myring + (r & 15) * RING_P;
       if (HALF) {
         const int tn = to_fix(cur, 268435456.0f);
@@ -204,14 +204,13 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
 #pragma unroll
         for (int j = 0; j < 9; ++j) S[5 + j] += gval(tb, j) - gval(ob, j);
       }
-      const unsigned s = q % NST, ph = (q / NST) & 1u;
-      mbar_wait(bars + NST + s, ph ^ 1u);                      // consumers have read the previous row in this stage
+      mbar_wait(bars + NST + s, ph);                           // consumers have read the previous row in this stage
       if (act) {
         // column vote sums over the 16 rows: S_b - S_{b+1} <= 2^28
-        int* dst = sS + s * STAGE_INTS + colour * VP + col;
+        int* dst = mydst + s * STAGE_INTS;
         if (HALF) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dst[(36 + 3 * i) * VP] = S[i] - S[i + 1];
+          for (int i = 0; i < 16; ++i) dst[(3 * i) * VP] = S[i] - S[i + 1];
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[(3 * i) * VP] = S[i] - S[i + 1];
@@ -221,6 +220,7 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + s);                    // release: this warp's column sums are in the stage
+      if (++s == NST) { s = 0; ph ^= 1u; }
     }
   }
 }
@@ -304,23 +304,32 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
   const int chr = actv ? ch : NH - 1;
   const int gtid = ctid - g * GROUP;
   const bool elected = (gtid == 0);
-  float* stg = sStg + g * (SW * CO);
+  float* stg0 = sStg + g * (2 * SW * CO);  // this group's two staging rows (alternating)
   float* rowsc = sRow + g * SW;
-  float* my = stg + (seg * 32) * CO + CH0 + ch;
+  const int myoff = (seg * 32) * CO + CH0 + ch;
   const int* myS = sS + chr * VP + seg * 32;
-  unsigned q = 0;
+  unsigned q = 0;                          // emission index of the next task's first row
+  unsigned par = 0;                        // staging buffer of this group's next row
   for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
     const Task k = task_decode(t, p);
     const bool xedge = (k.x0 == 0) || (k.x0 + SW + HR > p.w);
     const int vw = min(SW, p.w - k.x0);
-    float* orow = p.out + (((long long)k.n * p.h + k.y0) * p.w + k.x0) * CO;
     int nx = PK;                           // in-bounds columns of this thread's scale-table column (gtid < 64)
     if (gtid < SW) {
       const int gx = k.x0 + gtid;
       nx = min(max(min(gx + HR, p.w - 1) - max(gx - HL, 0) + 1, 0), PK);
     }
-    for (int y = k.y0; y < k.y1; ++y, ++q, orow += (long long)p.w * CO) {
-      if ((q & 1u) != (unsigned)g) continue;
+    // this group's rows of the task: those whose emission index q0 + (y - y0) has parity g
+    const unsigned q0 = q;
+    const int nrows = k.y1 - k.y0;
+    q += (unsigned)nrows;
+    const int first = (int)((g - q0) & 1u);
+    float* orow = p.out + (((long long)k.n * p.h + k.y0 + first) * p.w + k.x0) * CO;
+    const long long ostride = 2LL * p.w * CO;
+    for (int yy = first; yy < nrows; yy += 2, orow += ostride, par ^= 1u) {
+      const int y = k.y0 + yy;
+      const unsigned qq = q0 + (unsigned)yy;
+      float* stg = stg0 + par * (SW * CO);
       float fv = 0.f, fdy = 0.f, fdx = 0.f;
       int fpx = -1, fc = 0;
       if (FULL) {                          // img + Sobel of one (pixel, colour) of this row, loads issued early
@@ -333,21 +342,24 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
         }
       }
       const int ny = min(y + HR, p.h - 1) - max(y - HL, 0) + 1;
-      const unsigned s = q % NST, ph = (q / NST) & 1u;
+      const unsigned s = qq % NST, ph = (qq / NST) & 1u;
       mbar_wait(bars + s, ph);             // producers filled this stage
       const int4* vl = reinterpret_cast<const int4*>(myS + s * STAGE_INTS);
       float f[32];
-      if (xedge) window_sums<false>(vl, f, 0.f, bars + NST + s, lane);
-      else window_sums<true>(vl, f, sTab[ny * 17 + PK], bars + NST + s, lane);
-      if (elected) bulk_wait_read();       // the group's previous row has left the staging buffer
-      if (xedge && gtid < SW) rowsc[gtid] = sTab[ny * 17 + nx];
-      named_bar_sync(1 + g, GROUP);        // staging buffer free, scales visible
       if (xedge) {                         // the in-bounds count varies along the row: one scale per column
+        window_sums<false>(vl, f, 0.f, bars + NST + s, lane);
+        if (gtid < SW) rowsc[gtid] = sTab[ny * 17 + nx];
+        named_bar_sync(1 + g, GROUP);      // scales visible (the previous row's readers passed the row barrier)
         const float* rs = rowsc + seg * 32;
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] *= rs[j];
+      } else {
+        window_sums<true>(vl, f, sTab[ny * 17 + PK], bars + NST + s, lane);
       }
+      // the staging buffer was last read by the bulk store issued two rows ago, which the elected thread saw complete
+      // (its reads) before the previous row barrier
       if (actv) {
+        float* my = stg + myoff;
 #pragma unroll
         for (int j = 0; j < 32; ++j) my[j * CO] = f[j];
       }
@@ -358,7 +370,8 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
         o[4 + fc * 2] = fdx;
       }
       fence_async_smem();                  // staging writes -> visible to the bulk-copy (async) proxy
-      named_bar_sync(1 + g, GROUP);        // the whole row is staged
+      if (elected) bulk_wait_read();       // the previous row's store has left the OTHER staging buffer
+      named_bar_sync(1 + g, GROUP);        // the whole row is staged; the other buffer is free for the next row
       if (elected) {
         bulk_store(orow, stg, (unsigned)(vw * CO * 4));
         bulk_commit();
@@ -372,7 +385,7 @@ template <bool FULL>
 __global__ void __launch_bounds__(THREADS, 1) k_pool_slide(const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sStg = reinterpret_cast<float*>(smem_raw);                       // bulk-copy source: 16-byte aligned
-  int* sS = reinterpret_cast<int*>(sStg + 2 * SW * Cfg<FULL>::CO);
+  int* sS = reinterpret_cast<int*>(sStg + 4 * SW * Cfg<FULL>::CO);
   int* ring = sS + NST * STAGE_INTS;
   float* sRow = reinterpret_cast<float*>(ring + 16 * RING_P);
   float* sTab = sRow + 2 * SW;
