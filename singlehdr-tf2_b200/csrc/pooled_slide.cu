@@ -45,9 +45,10 @@ constexpr int NH = 84;                       // histogram channels: 3 * (4 + 8 +
 constexpr int VP = 84;                       // ints per channel line of a stage (79 + pad; 84 = 20 mod 32)
 constexpr int NST = 3;                       // column-sum stages
 constexpr int STAGE_INTS = NH * VP;          // 7056 ints = 28 KB
-constexpr int NPT = 3 * CW;                  // 237 (column, colour) pairs
-constexpr int RING_P = 3 * NPT + 1;          // ints per ring row: T4 | T8 | T16
-constexpr int NPW = 16, NCW = 12;            // producer / consumer warps
+constexpr int NCP = (CW + 1) / 2;            // 40 column pairs (the 80th column is padding)
+constexpr int NPT = 3 * NCP;                 // 120 (column pair, colour) items per producer half
+constexpr int RING_P = 3 * NPT;              // int2 per ring row: T4 | T8 | T16 of every item
+constexpr int NPW = 8, NCW = 12;             // producer / consumer warps
 constexpr int NPROD = NPW * 32, NCONS = NCW * 32, THREADS = NPROD + NCONS;
 constexpr int GROUP = NCONS / 2;             // threads of one consumer row group
 constexpr int CAPV = 1 << 24;                // vote 1.0
@@ -58,7 +59,7 @@ constexpr int TAB = 17 * 17 + 3;             // 1 / (ny * nx * 2^24) for ny, nx 
 template <bool FULL> struct Cfg {
   static constexpr int CO = FULL ? SHDR_FRONTEND_CH : SHDR_HIST_CH;   // floats per output pixel
   static constexpr int CH0 = FULL ? 9 : 0;                            // first histogram channel
-  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P + 4 * SW * CO + 2 * SW + TAB) * 4 + 2 * NST * 8;
+  static constexpr size_t SMEM = (size_t)(NST * STAGE_INTS + 16 * RING_P * 2 + 4 * SW * CO + 2 * SW + TAB) * 4 + 2 * NST * 8;
 };
 
 struct Params {
@@ -118,37 +119,39 @@ __device__ __forceinline__ int to_fix(float v, float scale) { return __float2int
 __device__ __forceinline__ int gval(int t, int j) { return __viaddmin_s32_relu(t, (1 << 23) - j * (1 << 24), CAPV); }
 
 // ------------------------------------------------------------------------------------------ producers
-// HALF 0: histograms B = 4 (5 G) and B = 8 (9 G) of one (column, colour); HALF 1: B = 16 (17 G).
+// One producer thread owns TWO adjacent columns of one colour (64-bit shared-memory accesses, half the per-row
+// bookkeeping per column).  HALF 0: histograms B = 4 (5 G) and B = 8 (9 G); HALF 1: B = 16 (17 G).
 template <int HALF>
-__device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, int* __restrict__ ring, uint64_t* bars,
+__device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, int2* __restrict__ ring, uint64_t* bars,
                                          int ptid) {
   constexpr int NG = HALF ? 17 : 14;
   const int rem = ptid - HALF * (NPROD / 2);
   const bool act = rem < NPT;
-  const int colour = act ? rem / CW : 0;
-  const int col = act ? rem - colour * CW : 0;
+  const int colour = act ? rem / NCP : 0;
+  const int cp = act ? rem - colour * NCP : 0;                   // columns 2*cp, 2*cp + 1
   const int lane = ptid & 31;
-  int* myring = ring + (HALF ? 2 * NPT : 0) + (act ? rem : 0);   // HALF 0: T4 at +0, T8 at +NPT
-  int* mydst = sS + (colour + (HALF ? 36 : 0)) * VP + col;       // this thread's first channel line, stage 0
+  int2* myring = ring + (HALF ? 2 * NPT : 0) + (act ? rem : 0);  // HALF 0: T4 at +0, T8 at +NPT
+  int2* mydst = reinterpret_cast<int2*>(sS + (colour + (HALF ? 36 : 0)) * VP) + cp;   // first channel line, stage 0
   const int h = p.h, rs3 = p.w * 3;
   const int pfoff = (PFD - 1) * rs3;
-  int S[NG];
+  int S0[NG], S1[NG];
   unsigned s = 0, ph = 1;                  // stage of the next emitted row; parity of its "empty" wait (first use passes)
   for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
     const Task k = task_decode(t, p);
-    const int gx = k.x0 - HL + col;
-    const bool xok = act && gx >= 0 && gx < p.w;
-    const float* src = p.img + ((long long)k.n * h * p.w + gx) * 3 + colour;
+    const int gx = k.x0 - HL + 2 * cp;
+    const bool xok0 = act && gx >= 0 && gx < p.w;
+    const bool xok1 = act && gx + 1 >= 0 && gx + 1 < p.w && 2 * cp + 1 < CW;
+    const float* src = p.img + ((long long)k.n * h * p.w + gx) * 3 + colour;   // column 2*cp; the next one is src + 3
     // The register prefetch (one row ahead) only covers an L2 hit; under the write stream a DRAM read takes longer
     // than a row, so every eighth column also pulls the row PFD rows ahead into L2 (a row of the strip is 948 B).
-    const bool pf = xok && colour == 0 && ((col & 7) == 0 || col == CW - 1);
+    const bool pf = xok0 && colour == 0 && ((cp & 3) == 0 || cp == NCP - 1);
 #pragma unroll
-    for (int j = 0; j < NG; ++j) S[j] = 0;
+    for (int j = 0; j < NG; ++j) { S0[j] = 0; S1[j] = 0; }
     if (act) {
 #pragma unroll
-      for (int s = 0; s < 16; ++s) {
-        myring[s * RING_P] = T_OUT;
-        if (!HALF) myring[s * RING_P + NPT] = T_OUT;
+      for (int i = 0; i < 16; ++i) {
+        myring[i * RING_P] = make_int2(T_OUT, T_OUT);
+        if (!HALF) myring[i * RING_P + NPT] = make_int2(T_OUT, T_OUT);
       }
     }
     int r = max(k.y0 - HL, 0);             // the row that enters next; rows are addressed as src[off], off = row * rs3
@@ -156,66 +159,82 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
 #pragma unroll 1
     for (int i = 1; i < PFD; ++i)
       if (pf && r + i < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + i * rs3));
-    float nxt = (xok && r < h) ? __ldg(src + off) : -2.0f;     // out of the image: no vote
+    float n0 = (xok0 && r < h) ? __ldg(src + off) : -2.0f;     // out of the image: no vote
+    float n1 = (xok1 && r < h) ? __ldg(src + off + 3) : -2.0f;
+    float c0, c1;
     // one row step: clamp the row loaded during the previous step (NaN -> -2: votes 0, like tf.where on a NaN
     // compare), start the load of the next row and the L2 prefetch PFD rows ahead
-    auto advance = [&]() -> float {
-      const float cur = fminf(fmaxf(nxt, -2.0f), 3.0f);
+    auto advance = [&]() {
+      c0 = fminf(fmaxf(n0, -2.0f), 3.0f);
+      c1 = fminf(fmaxf(n1, -2.0f), 3.0f);
       off += rs3;
-      nxt = (xok && r + 1 < h) ? __ldg(src + off) : -2.0f;
+      const bool rok = r + 1 < h;
+      n0 = (xok0 && rok) ? __ldg(src + off) : -2.0f;
+      n1 = (xok1 && rok) ? __ldg(src + off + 3) : -2.0f;
       if (pf && r + PFD < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + pfoff));
-      return cur;
     };
     // warm-up: rows y0-7 .. y0+7 enter, nothing leaves, nothing is emitted
     for (; r <= k.y0 + HL; ++r) {
-      const float cur = advance();
-      int* rs = myring + (r & 15) * RING_P;
+      advance();
+      int2* rs = myring + (r & 15) * RING_P;
       if (HALF) {
-        const int tn = to_fix(cur, 268435456.0f);
+        const int2 tn = make_int2(to_fix(c0, 268435456.0f), to_fix(c1, 268435456.0f));
         if (act) rs[0] = tn;
 #pragma unroll
-        for (int j = 0; j < 17; ++j) S[j] += gval(tn, j);
+        for (int j = 0; j < 17; ++j) { S0[j] += gval(tn.x, j); S1[j] += gval(tn.y, j); }
       } else {
-        const int ta = to_fix(cur, 67108864.0f), tb = to_fix(cur, 134217728.0f);
+        const int2 ta = make_int2(to_fix(c0, 67108864.0f), to_fix(c1, 67108864.0f));
+        const int2 tb = make_int2(to_fix(c0, 134217728.0f), to_fix(c1, 134217728.0f));
         if (act) { rs[0] = ta; rs[NPT] = tb; }
 #pragma unroll
-        for (int j = 0; j < 5; ++j) S[j] += gval(ta, j);
+        for (int j = 0; j < 5; ++j) { S0[j] += gval(ta.x, j); S1[j] += gval(ta.y, j); }
 #pragma unroll
-        for (int j = 0; j < 9; ++j) S[5 + j] += gval(tb, j);
+        for (int j = 0; j < 9; ++j) { S0[5 + j] += gval(tb.x, j); S1[5 + j] += gval(tb.y, j); }
       }
     }
     // steady state: row r = y+8 enters, row y-8 leaves, row y is emitted
     const int rend = k.y1 + HR;
     for (; r < rend; ++r) {
-      const float cur = advance();
-      int* rs = myring + (r & 15) * RING_P;
+      advance();
+      int2* rs = myring + (r & 15) * RING_P;
       if (HALF) {
-        const int tn = to_fix(cur, 268435456.0f);
-        const int to = rs[0];
+        const int2 tn = make_int2(to_fix(c0, 268435456.0f), to_fix(c1, 268435456.0f));
+        const int2 to = rs[0];
         if (act) rs[0] = tn;
 #pragma unroll
-        for (int j = 0; j < 17; ++j) S[j] += gval(tn, j) - gval(to, j);
+        for (int j = 0; j < 17; ++j) {
+          S0[j] += gval(tn.x, j) - gval(to.x, j);
+          S1[j] += gval(tn.y, j) - gval(to.y, j);
+        }
       } else {
-        const int ta = to_fix(cur, 67108864.0f), tb = to_fix(cur, 134217728.0f);
-        const int oa = rs[0], ob = rs[NPT];
+        const int2 ta = make_int2(to_fix(c0, 67108864.0f), to_fix(c1, 67108864.0f));
+        const int2 tb = make_int2(to_fix(c0, 134217728.0f), to_fix(c1, 134217728.0f));
+        const int2 oa = rs[0], ob = rs[NPT];
         if (act) { rs[0] = ta; rs[NPT] = tb; }
 #pragma unroll
-        for (int j = 0; j < 5; ++j) S[j] += gval(ta, j) - gval(oa, j);
+        for (int j = 0; j < 5; ++j) {
+          S0[j] += gval(ta.x, j) - gval(oa.x, j);
+          S1[j] += gval(ta.y, j) - gval(oa.y, j);
+        }
 #pragma unroll
-        for (int j = 0; j < 9; ++j) S[5 + j] += gval(tb, j) - gval(ob, j);
+        for (int j = 0; j < 9; ++j) {
+          S0[5 + j] += gval(tb.x, j) - gval(ob.x, j);
+          S1[5 + j] += gval(tb.y, j) - gval(ob.y, j);
+        }
       }
       mbar_wait(bars + NST + s, ph);                           // consumers have read the previous row in this stage
       if (act) {
         // column vote sums over the 16 rows: S_b - S_{b+1} <= 2^28
-        int* dst = mydst + s * STAGE_INTS;
+        int2* dst = mydst + s * (STAGE_INTS / 2);
         if (HALF) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dst[(3 * i) * VP] = S[i] - S[i + 1];
+          for (int i = 0; i < 16; ++i) dst[(3 * i) * (VP / 2)] = make_int2(S0[i] - S0[i + 1], S1[i] - S1[i + 1]);
         } else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[(3 * i) * VP] = S[i] - S[i + 1];
+          for (int i = 0; i < 4; ++i) dst[(3 * i) * (VP / 2)] = make_int2(S0[i] - S0[i + 1], S1[i] - S1[i + 1]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[(12 + 3 * i) * VP] = S[5 + i] - S[6 + i];
+          for (int i = 0; i < 8; ++i)
+            dst[(12 + 3 * i) * (VP / 2)] = make_int2(S0[5 + i] - S0[6 + i], S1[5 + i] - S1[6 + i]);
         }
       }
       __syncwarp();
@@ -386,7 +405,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_pool_slide(const __grid_constant
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* sStg = reinterpret_cast<float*>(smem_raw);                       // bulk-copy source: 16-byte aligned
   int* sS = reinterpret_cast<int*>(sStg + 4 * SW * Cfg<FULL>::CO);
-  int* ring = sS + NST * STAGE_INTS;
+  int2* ring = reinterpret_cast<int2*>(sS + NST * STAGE_INTS);
   float* sRow = reinterpret_cast<float*>(ring + 16 * RING_P);
   float* sTab = sRow + 2 * SW;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sTab + TAB);               // full[NST], empty[NST]
