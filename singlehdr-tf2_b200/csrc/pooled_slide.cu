@@ -67,6 +67,9 @@ struct Params {
   float* out;
   int n, h, w;
   int nsx, nsy, rseg, ntasks;
+  // +1 and -1 as OPAQUE kernel parameters: "s += g * one" compiles to IMAD (fma pipe) where "s += g" would be an IADD3
+  // on the alu pipe, which VIADDMNMX / I2FP / compares already saturate (pipe balance)
+  int one, mone;
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -134,6 +137,7 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
   int2* mydst = reinterpret_cast<int2*>(sS + (colour + (HALF ? 36 : 0)) * VP) + cp;   // first channel line, stage 0
   const int h = p.h, rs3 = p.w * 3;
   const int pfoff = (PFD - 1) * rs3;
+  const int one = p.one, mone = p.mone;
   int S0[NG], S1[NG];
   unsigned s = 0, ph = 1;                  // stage of the next emitted row; parity of its "empty" wait (first use passes)
   for (int t = blockIdx.x; t < p.ntasks; t += gridDim.x) {
@@ -203,8 +207,8 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
         if (act) rs[0] = tn;
 #pragma unroll
         for (int j = 0; j < 17; ++j) {
-          S0[j] += gval(tn.x, j) - gval(to.x, j);
-          S1[j] += gval(tn.y, j) - gval(to.y, j);
+          S0[j] += gval(tn.x, j) * one; S0[j] += gval(to.x, j) * mone;
+          S1[j] += gval(tn.y, j) * one; S1[j] += gval(to.y, j) * mone;
         }
       } else {
         const int2 ta = make_int2(to_fix(c0, 67108864.0f), to_fix(c1, 67108864.0f));
@@ -213,13 +217,13 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
         if (act) { rs[0] = ta; rs[NPT] = tb; }
 #pragma unroll
         for (int j = 0; j < 5; ++j) {
-          S0[j] += gval(ta.x, j) - gval(oa.x, j);
-          S1[j] += gval(ta.y, j) - gval(oa.y, j);
+          S0[j] += gval(ta.x, j) * one; S0[j] += gval(oa.x, j) * mone;
+          S1[j] += gval(ta.y, j) * one; S1[j] += gval(oa.y, j) * mone;
         }
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
-          S0[5 + j] += gval(tb.x, j) - gval(ob.x, j);
-          S1[5 + j] += gval(tb.y, j) - gval(ob.y, j);
+          S0[5 + j] += gval(tb.x, j) * one; S0[5 + j] += gval(ob.x, j) * mone;
+          S1[5 + j] += gval(tb.y, j) * one; S1[5 + j] += gval(ob.y, j) * mone;
         }
       }
       mbar_wait(bars + NST + s, ph);                           // consumers have read the previous row in this stage
@@ -452,6 +456,7 @@ bool pool_slide_supported(const float* out, int w, const int* bins, int nbins, b
 int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool full93, int dev, cudaStream_t st) {
   sl::Params p;
   p.img = img; p.out = out; p.n = n; p.h = h; p.w = w;
+  p.one = 1; p.mone = -1;
   p.nsx = (w + sl::SW - 1) / sl::SW;
   const int sms = sm_count(dev);
   // row segments: every task pays a warm-up of 15 rows (about 6 rows' worth of work); pick the split that minimises
