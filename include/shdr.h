@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SHDR_VERSION 100            /* 0.1.0 */
+#define SHDR_VERSION 200            /* 0.2.0 */
 
 #define SHDR_OK               0
 #define SHDR_ERR_INVALID     -1     /* bad argument (shape, NULL pointer, alignment ...) */
@@ -104,6 +104,45 @@ int shdr_apply_rf_f32(const float* x, const float* rf, float* y, int b,
 int shdr_linearize_f32(const float* x, const float* w, float* y, float* curve_out,
                        int b, long long elems_per_item, void* stream);
 
+/* The steps either side of apply_rf in the inference graph, in the same pass
+ * (test_real_refinement.py:91-101): x is [b, pixels_per_item, 3] (RGB pixels);
+ *   c = clip_by_value(x, 0, 1)                           if clip != 0   (:91)
+ *   y = apply_rf(c, rf)                                                  (:95)
+ *   alpha = min(1, max(0, max_c(y) - 1 + thr) / thr), tiled over the 3 channels   (:98-101)
+ * clipped_out (C_pred, [b,pixels,3]) and alpha_out ([b,pixels,3]) may be NULL. */
+int shdr_apply_rf_ex_f32(const float* x, const float* rf, float* y, float* clipped_out,
+                         float* alpha_out, int b, long long pixels_per_item, int k,
+                         int clip, float thr, void* stream);
+/* shdr_linearize_f32 with the same fused neighbours (curve from the PCA weights w[b,11]). */
+int shdr_linearize_ex_f32(const float* x, const float* w, float* y, float* curve_out,
+                          float* clipped_out, float* alpha_out, int b,
+                          long long pixels_per_item, int clip, float thr, void* stream);
+
+/* ---- (C) reverse-mode gradients (training steps: train.py:186-194,
+ *          joint_training.py:156-186, finetune_real_dataset.py:149-178) -------------
+ * Each restates what TensorFlow's autodiff computes for the reference's op sequence. */
+
+/* gradient of tf_utils.apply_rf (tf_utils.py:54-105): gy has the shape of x.
+ * gx (nullable, shape of x) = gy (k-1) (rf[i1] - rf[i0]);
+ * grf (nullable, [b,k], overwritten) = scatter-add of gy (y1-y) at i0 and gy (y-y0) at i1
+ * (fp32 atomics: the summation order is not deterministic, like TF's gather_nd gradient). */
+int shdr_apply_rf_bwd_f32(const float* x, const float* rf, const float* gy, float* gx,
+                          float* grf, int b, long long elems_per_item, int k, void* stream);
+/* gradient of model._increase (linearization_net.py:368-392) w.r.t. rf[b,k], 2 <= k <= 24576. */
+int shdr_increase_bwd_f32(const float* rf, const float* gout, float* grf, int b, int k,
+                          void* stream);
+/* gradient of shdr_invcrf_build_f32 w.r.t. w[b,11]: gcurve[b,1024] is the gradient of the
+ * curve (monotone = 0: of g0 + hinv.w; monotone != 0: of _increase(g0 + hinv.w)). */
+int shdr_invcrf_build_bwd_f32(const float* w, const float* gcurve, float* gw, int b,
+                              int monotone, void* stream);
+/* gradient of shdr_frontend_f32(pool_k = 0) w.r.t. img: gfeat[n,h,w,93] -> gimg[n,h,w,3]
+ * (identity slice + soft-histogram slopes + transposed REFLECT Sobel). */
+int shdr_frontend_bwd_f32(const float* img, const float* gfeat, float* gimg, int n, int h,
+                          int w, void* stream);
+/* gradient of shdr_soft_hist_f32(pool_k = 0, dense output) w.r.t. img: ghist[n,h,w,c*bins]. */
+int shdr_soft_hist_bwd_f32(const float* img, const float* ghist, float* gimg, int n, int h,
+                           int w, int c, int bins, void* stream);
+
 /* ---- DLPack entry points ------------------------------------------------------
  * Same operations on DLManagedTensor* (DLPack v0.x ABI, as produced by
  * tf.experimental.dlpack.to_dlpack / torch.utils.dlpack.to_dlpack).  Inputs are
@@ -130,6 +169,12 @@ int shdr_dl_alloc_f32(const int64_t* shape, int ndim, int device,
                       struct DLManagedTensor** out);
 /* run the deleter of a tensor returned above that was never handed to a consumer */
 void shdr_dl_release(struct DLManagedTensor* t);
+/* Producer/consumer ordering of a library-owned tensor without a device-wide sync: every
+ * shdr_dl_* op records a "ready" event on its stream; shdr_dl_mark_ready does the same for
+ * work the caller enqueued itself.  shdr_dl_wait_ready makes `consumer_stream` wait for it
+ * (on_host = 0) or blocks the host until the tensor's producer has finished (on_host != 0). */
+int shdr_dl_mark_ready(struct DLManagedTensor* t, void* stream);
+int shdr_dl_wait_ready(struct DLManagedTensor* t, void* consumer_stream, int on_host);
 /* address of a `void (*)(PyObject*)` usable as PyCapsule destructor for a "dltensor" capsule:
  * it runs the tensor's deleter unless a consumer renamed the capsule ("used_dltensor"). */
 void* shdr_dl_capsule_destructor(void);

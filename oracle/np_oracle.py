@@ -220,3 +220,131 @@ def linearize(x, w, g0, hinv, dtype=np.float32):
     (linearization_net.py:325-328, test_real_refinement.py:94-95)."""
     curve = increase(invcrf_pca_w_2_invcrf(w, g0, hinv, dtype), dtype)
     return apply_rf(x, curve, dtype), curve
+
+
+# --------------------------------------------------------------------------
+# (C) the steps either side of apply_rf in the inference graph
+# --------------------------------------------------------------------------
+def clip01(x, dtype=np.float32):
+    """``tf.clip_by_value(pred_deq, 0, 1)``, test_real_refinement.py:91."""
+    return np.minimum(np.maximum(np.asarray(x, dtype=dtype), dtype(0.0)), dtype(1.0))
+
+
+def alpha_mask(b_pred, thr, dtype=np.float32):
+    """The hallucination blend mask of test_real_refinement.py:98-101 (train.py:207-211):
+    ``alpha = reduce_max(B_pred, axis=3)``; ``min(1, max(0, alpha - 1 + thr) / thr)``; tiled over 3 channels."""
+    b_pred = np.asarray(b_pred, dtype=dtype)
+    a = np.max(b_pred, axis=3)
+    a = np.minimum(dtype(1.0), np.maximum(dtype(0.0), (a - dtype(1.0)) + dtype(thr)) / dtype(thr))
+    return np.tile(a[..., None], (1, 1, 1, 3)).astype(dtype)
+
+
+def linearize_ex(x, rf, thr, clip=True, dtype=np.float32):
+    """clip -> apply_rf -> alpha mask, as the inference graph chains them.  Returns (C_pred, B_pred, alpha)."""
+    c = clip01(x, dtype) if clip else np.asarray(x, dtype=dtype)
+    y = apply_rf(c, rf, dtype)
+    return c, y, alpha_mask(y, thr, dtype)
+
+
+# --------------------------------------------------------------------------
+# (D) reverse-mode gradients: what TensorFlow's autodiff computes for the reference's op sequences
+#     (train.py:186-194, joint_training.py:156-186, finetune_real_dataset.py:149-178).  [TF-sem]: floor / cast /
+#     less have no gradient; abs -> sign (0 at 0); where routes to the taken branch; reduce_min splits evenly among
+#     ties; gather_nd -> scatter-add; relu'(0) = 0.
+# --------------------------------------------------------------------------
+def apply_rf_grad(x, rf, gy, dtype=np.float64, index_dtype=np.float32):
+    """Gradient of :func:`apply_rf` w.r.t. ``x`` and ``rf``.  The positions ``y = (k-1) x``, their floor and the two
+    weights are evaluated in ``index_dtype`` (float32: the bins and weights the fp32 forward pass used -- a value of
+    ``y`` within rounding of an integer must land in the same bin as in the forward); products and sums in ``dtype``."""
+    rf = np.asarray(rf, dtype=dtype); gy = np.asarray(gy, dtype=dtype)
+    b, k = rf.shape
+    xf = np.asarray(x, dtype=index_dtype).reshape(b, -1)
+    gf = gy.reshape(b, -1)
+    y = index_dtype(k - 1) * xf
+    y0 = np.floor(y); y1 = y0 + index_dtype(1.0)
+    with np.errstate(invalid="ignore"):
+        i0 = np.clip(y0.astype(np.int64), 0, k - 1); i1 = np.clip(y1.astype(np.int64), 0, k - 1)
+    w0 = (y1 - y).astype(dtype); w1 = (y - y0).astype(dtype)
+    rows = np.arange(b)[:, None]
+    gx = dtype(k - 1) * (gf * rf[rows, i1] - gf * rf[rows, i0])
+    grf = np.zeros_like(rf)
+    np.add.at(grf, (np.broadcast_to(rows, i0.shape), i0), gf * w0)
+    np.add.at(grf, (np.broadcast_to(rows, i1.shape), i1), gf * w1)
+    return gx.reshape(np.shape(x)), grf
+
+
+def increase_grad(rf, gout, dtype=np.float64):
+    """Gradient of :func:`increase` w.r.t. ``rf``."""
+    rf = np.asarray(rf, dtype=dtype); gout = np.asarray(gout, dtype=dtype)
+    g = rf[:, 1:] - rf[:, :-1]
+    m = np.min(g, axis=-1, keepdims=True)
+    r = np.maximum(-m, 0)
+    u = g + r
+    s = np.sum(u, axis=-1, keepdims=True)
+    n = u / s
+    dn = np.cumsum(gout[:, :0:-1], axis=-1)[:, ::-1]            # reverse inclusive cumsum of gout[:, 1:]
+    du = (dn - np.sum(dn * n, axis=-1, keepdims=True)) / s
+    dr = np.sum(du, axis=-1, keepdims=True)
+    tie = (g == m)
+    dg = du + np.where(m < 0, -dr, 0) * tie / np.sum(tie, axis=-1, keepdims=True)
+    grf = np.zeros_like(rf)
+    grf[:, 1:] += dg
+    grf[:, :-1] -= dg
+    return grf
+
+
+def invcrf_pca_grad(gcurve, hinv, dtype=np.float64):
+    """Gradient of :func:`invcrf_pca_w_2_invcrf` w.r.t. ``w``: ``gcurve [b,1024] @ hinv [1024,11]``."""
+    return np.asarray(gcurve, dtype=dtype) @ np.asarray(hinv, dtype=dtype)
+
+
+def histogram_layer_grad(img, ghist, max_bin, dtype=np.float64):
+    """Gradient of :func:`histogram_layer` w.r.t. ``img``; the compare uses the fp32 forward's values so that the
+    taken branch is the one the fp32 forward took."""
+    img32 = np.asarray(img, dtype=np.float32)
+    c = img32.shape[-1]
+    thr = np.float32(1.0 / max_bin)
+    centers = hist_centers(max_bin, np.float32)
+    gimg = np.zeros(img32.shape, dtype=dtype)
+    ghist = np.asarray(ghist, dtype=dtype)
+    for i in range(max_bin):
+        d = img32 - centers[i]
+        taken = np.abs(d) < thr
+        gimg += np.where(taken, -dtype(max_bin) * np.sign(d).astype(dtype) * ghist[..., i * c:(i + 1) * c], 0)
+    return gimg
+
+
+def sobel_edges6_grad(gedge, shape, dtype=np.float64):
+    """Gradient of :func:`sobel_edges6` w.r.t. ``img``: scatter every tap of the REFLECT-padded correlation back."""
+    n, h, w, c = shape
+    ge = np.asarray(gedge, dtype=dtype).reshape(n, h, w, c, 2)
+    gp = np.zeros((n, h + 2, w + 2, c), dtype=dtype)
+    for k, ker in enumerate((_KY, _KX)):
+        for r in range(3):
+            for s in range(3):
+                if ker[r][s] != 0.0:
+                    gp[:, r:r + h, s:s + w, :] += dtype(ker[r][s]) * ge[..., k]
+    g = gp[:, 1:-1, 1:-1, :].copy()
+    # fold the reflected border back: padded row 0 mirrors row 1, padded row h+1 mirrors row h-2 (same for columns)
+    gfull = gp
+    g[:, 1, :, :] += gfull[:, 0, 1:-1, :]
+    g[:, h - 2, :, :] += gfull[:, h + 1, 1:-1, :]
+    g[:, :, 1, :] += gfull[:, 1:-1, 0, :]
+    g[:, :, w - 2, :] += gfull[:, 1:-1, w + 1, :]
+    g[:, 1, 1, :] += gfull[:, 0, 0, :]
+    g[:, 1, w - 2, :] += gfull[:, 0, w + 1, :]
+    g[:, h - 2, 1, :] += gfull[:, h + 1, 0, :]
+    g[:, h - 2, w - 2, :] += gfull[:, h + 1, w + 1, :]
+    return g
+
+
+def frontend_grad(img, gfeat, bins=BINS, dtype=np.float64):
+    """Gradient of :func:`frontend` (un-pooled) w.r.t. ``img``."""
+    img32 = np.asarray(img, dtype=np.float32)
+    gfeat = np.asarray(gfeat, dtype=dtype)
+    g = gfeat[..., :3].copy() + sobel_edges6_grad(gfeat[..., 3:9], img32.shape, dtype)
+    off = 9
+    for b in bins:
+        g += histogram_layer_grad(img32, gfeat[..., off:off + 3 * b], b, dtype)
+        off += 3 * b
+    return g

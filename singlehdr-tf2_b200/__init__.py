@@ -11,12 +11,13 @@ from ._native import ShdrError, device_count, launch_count, require_gpu   # noqa
 from .device import DeviceArray, PinnedArray, Stream, Event, synchronize  # noqa: F401
 from .layers import (                                                      # noqa: F401
     BINS, POOL_K, sobel_edges6, histogram_layer, frontend, hist_multi, parse_invemor,
-    set_emor_table, invcrf_pca_w_2_invcrf, invcrf_build, _increase, apply_rf, linearize,
+    set_emor_table, invcrf_pca_w_2_invcrf, invcrf_build, _increase, apply_rf, linearize, linearize_ex,
+    apply_rf_bwd, _increase_bwd, invcrf_build_bwd, frontend_bwd, histogram_layer_bwd,
     AEInvcrfDecodeNet, model,
 )
 from .host import (                                                        # noqa: F401
     HostPipeline, frontend_host, hist_multi_host, linearize_host, apply_rf_host,
 )
-from .sharding import shard_range, row_tiles, gather_to_all               # noqa: F401
+from .sharding import shard_range, row_tiles                              # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -51,6 +51,13 @@ SIGNATURES = {
     "shdr_increase_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "shdr_apply_rf_f32": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),
     "shdr_linearize_f32": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp]),
+    "shdr_apply_rf_ex_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, C.c_float, _vp]),
+    "shdr_linearize_ex_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, C.c_float, _vp]),
+    "shdr_apply_rf_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
+    "shdr_increase_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "shdr_invcrf_build_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "shdr_frontend_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "shdr_soft_hist_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "shdr_dl_frontend": (_i, [_dl, _i, _vp, _dlp]),
     "shdr_dl_sobel6": (_i, [_dl, _vp, _dlp]),
     "shdr_dl_soft_hist": (_i, [_dl, _i, _i, _vp, _dlp]),
@@ -59,6 +66,8 @@ SIGNATURES = {
     "shdr_dl_apply_rf": (_i, [_dl, _dl, _vp, _dlp]),
     "shdr_dl_alloc_f32": (_i, [C.POINTER(C.c_int64), _i, _i, _dlp]),
     "shdr_dl_release": (None, [_dl]),
+    "shdr_dl_mark_ready": (_i, [_dl, _vp]),
+    "shdr_dl_wait_ready": (_i, [_dl, _vp, _i]),
     "shdr_dl_capsule_destructor": (_vp, []),
     "shdr_malloc": (_i, [_dlp, _sz, _i]),
     "shdr_free": (_i, [_vp, _i]),

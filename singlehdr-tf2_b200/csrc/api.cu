@@ -84,8 +84,10 @@ int emor_device_table(int dev, const float** g0, const float** hinv) {
   if ((int)g_tab_dev.size() <= dev) g_tab_dev.resize(dev + 1);
   DevTab& t = g_tab_dev[dev];
   const size_t bytes = g_tab_host.size() * sizeof(float);
-  if (t.ptr == nullptr) SHDR_CUDA(cudaMalloc((void**)&t.ptr, bytes));
   if (t.version != g_tab_version) {
+    // a changed table goes to a NEW buffer: kernels already enqueued on other streams keep reading the old one
+    // (it is leaked on purpose -- 49 KB per table change, which happens once per process in practice)
+    SHDR_CUDA(cudaMalloc((void**)&t.ptr, bytes));
     // one-time 49 KB upload per device (g0, then hinv TRANSPOSED to [11][1024] so that the curve kernel's
     // per-sample reads are coalesced); synchronous so the host vector may change afterwards
     std::vector<float> dev_img(g_tab_host.size());
@@ -154,27 +156,38 @@ struct OwnedTensor {
   DLManagedTensor m;
   int64_t shape[8];
   int dev;
+  cudaEvent_t ready;      // recorded after the producing work; nullptr until the first mark
 };
+// The deleter runs when the DLPack consumer drops the tensor.  The consumer's stream is unknown here and its kernels
+// may still be queued, so the free is a plain cudaFree: it waits for the device, which is the only ordering that is
+// safe against every consumer.  (Allocation is stream-ordered and does not synchronise.)
 static void owned_deleter(DLManagedTensor* m) {
   OwnedTensor* o = static_cast<OwnedTensor*>(m->manager_ctx);
-  if (o->m.dl_tensor.data) {
-    DeviceGuard g(o->dev);
-    cudaFree(o->m.dl_tensor.data);
-  }
+  DeviceGuard g(o->dev);
+  if (o->ready) cudaEventDestroy(o->ready);
+  if (o->m.dl_tensor.data) cudaFree(o->m.dl_tensor.data);
   delete o;
 }
-static int dl_alloc(const int64_t* shape, int ndim, int dev, DLManagedTensor** out) {
+static OwnedTensor* owned_of(DLManagedTensor* t) {
+  return (t && t->deleter == owned_deleter) ? static_cast<OwnedTensor*>(t->manager_ctx) : nullptr;
+}
+static int dl_alloc(const int64_t* shape, int ndim, int dev, cudaStream_t st, DLManagedTensor** out,
+                    bool stream_ordered = true) {
   SHDR_REQUIRE(out != nullptr && ndim >= 1 && ndim <= 8, "dl_alloc: bad arguments");
   int64_t numel = 1;
   for (int i = 0; i < ndim; ++i) { SHDR_REQUIRE(shape[i] >= 0, "dl_alloc: negative dim"); numel *= shape[i]; }
   OwnedTensor* o = new OwnedTensor();
   memset(&o->m, 0, sizeof(o->m));
   o->dev = dev;
+  o->ready = nullptr;
   void* p = nullptr;
   {
     DeviceGuard g(dev);
     if (g.status != SHDR_OK) { delete o; return g.status; }
-    cudaError_t e = cudaMalloc(&p, (size_t)(numel > 0 ? numel : 1) * sizeof(float));
+    // stream-ordered allocation from the device's default pool: no implicit device synchronisation, and blocks freed
+    // by cudaFree are reused without going back to the driver
+    const size_t bytes = (size_t)(numel > 0 ? numel : 1) * sizeof(float);
+    cudaError_t e = stream_ordered ? cudaMallocAsync(&p, bytes, st) : cudaMalloc(&p, bytes);
     if (e != cudaSuccess) { delete o; return cuda_fail(e, "cudaMalloc(output tensor)"); }
   }
   for (int i = 0; i < ndim; ++i) o->shape[i] = shape[i];
@@ -190,6 +203,15 @@ static int dl_alloc(const int64_t* shape, int ndim, int dev, DLManagedTensor** o
   o->m.manager_ctx = o;
   o->m.deleter = owned_deleter;
   *out = &o->m;
+  return SHDR_OK;
+}
+static int dl_mark_ready(DLManagedTensor* t, cudaStream_t st) {
+  OwnedTensor* o = owned_of(t);
+  SHDR_REQUIRE(o != nullptr, "dl_mark_ready: not a tensor allocated by this library");
+  DeviceGuard g(o->dev);
+  if (g.status != SHDR_OK) return g.status;
+  if (!o->ready) SHDR_CUDA(cudaEventCreateWithFlags(&o->ready, cudaEventDisableTiming));
+  SHDR_CUDA(cudaEventRecord(o->ready, st));
   return SHDR_OK;
 }
 
@@ -216,7 +238,11 @@ extern "C" int shdr_set_emor_table(const float* g0_host, const float* hinv_host,
   SHDR_REQUIRE(s == SHDR_EMOR_SAMPLES && ncomp == SHDR_EMOR_NCOMP,
                "set_emor_table: this build needs s=%d, ncomp=%d (got %d, %d)", SHDR_EMOR_SAMPLES, SHDR_EMOR_NCOMP, s, ncomp);
   std::lock_guard<std::mutex> lk(g_tab_mu);
-  g_tab_host.resize((size_t)s * (1 + ncomp));
+  const size_t n = (size_t)s * (1 + ncomp);
+  if (g_tab_host.size() == n && memcmp(g_tab_host.data(), g0_host, (size_t)s * sizeof(float)) == 0 &&
+      memcmp(g_tab_host.data() + s, hinv_host, (size_t)s * ncomp * sizeof(float)) == 0)
+    return SHDR_OK;                      // same table again (the reference re-parses it on every call): nothing to do
+  g_tab_host.resize(n);
   memcpy(g_tab_host.data(), g0_host, (size_t)s * sizeof(float));
   memcpy(g_tab_host.data() + s, hinv_host, (size_t)s * ncomp * sizeof(float));
   ++g_tab_version;
@@ -252,9 +278,26 @@ static void capsule_destructor(void* pyobj) {
 }
 extern "C" void* shdr_dl_capsule_destructor(void) { return (void*)&capsule_destructor; }
 
+extern "C" int shdr_dl_mark_ready(struct DLManagedTensor* t, void* stream) {
+  return dl_mark_ready(t, (cudaStream_t)stream);
+}
+extern "C" int shdr_dl_wait_ready(struct DLManagedTensor* t, void* consumer_stream, int on_host) {
+  OwnedTensor* o = owned_of(t);
+  SHDR_REQUIRE(o != nullptr, "dl_wait_ready: not a tensor allocated by this library");
+  DeviceGuard g(o->dev);
+  if (g.status != SHDR_OK) return g.status;
+  if (!o->ready) {                       // producer unknown (caller enqueued work without marking): be conservative
+    SHDR_CUDA(cudaDeviceSynchronize());
+    return SHDR_OK;
+  }
+  if (on_host) SHDR_CUDA(cudaEventSynchronize(o->ready));
+  else SHDR_CUDA(cudaStreamWaitEvent((cudaStream_t)consumer_stream, o->ready, 0));
+  return SHDR_OK;
+}
+
 extern "C" int shdr_dl_alloc_f32(const int64_t* shape, int ndim, int device, struct DLManagedTensor** out) {
   SHDR_REQUIRE(shape != nullptr, "dl_alloc: NULL shape");
-  return dl_alloc(shape, ndim, device, out);
+  return dl_alloc(shape, ndim, device, (cudaStream_t)0, out, false);   // the caller's stream is unknown: plain cudaMalloc
 }
 
 extern "C" int shdr_dl_frontend(const struct DLManagedTensor* img, int pool_k, void* stream, struct DLManagedTensor** out) {
@@ -263,8 +306,9 @@ extern "C" int shdr_dl_frontend(const struct DLManagedTensor* img, int pool_k, v
   DL_TRY(img_dims(v, "frontend", &n, &h, &w, &c));
   SHDR_REQUIRE(c == 3, "frontend: img must have 3 channels (got %d)", c);
   int64_t shp[4] = {n, h, w, SHDR_FRONTEND_CH};
-  DL_TRY(dl_alloc(shp, 4, v.dev, out));
+  DL_TRY(dl_alloc(shp, 4, v.dev, (cudaStream_t)stream, out));
   DL_RUN(out, shdr_frontend_f32(v.p, (float*)(*out)->dl_tensor.data, n, h, w, pool_k, stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }
 
@@ -273,8 +317,9 @@ extern "C" int shdr_dl_sobel6(const struct DLManagedTensor* img, void* stream, s
   DL_TRY(dl_view(img, "sobel6", &v));
   DL_TRY(img_dims(v, "sobel6", &n, &h, &w, &c));
   int64_t shp[4] = {n, h, w, 2 * (int64_t)c};
-  DL_TRY(dl_alloc(shp, 4, v.dev, out));
+  DL_TRY(dl_alloc(shp, 4, v.dev, (cudaStream_t)stream, out));
   DL_RUN(out, shdr_sobel6_f32(v.p, (float*)(*out)->dl_tensor.data, n, h, w, c, 2 * c, 0, stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }
 
@@ -285,8 +330,9 @@ extern "C" int shdr_dl_soft_hist(const struct DLManagedTensor* img, int bins, in
   DL_TRY(img_dims(v, "soft_hist", &n, &h, &w, &c));
   SHDR_REQUIRE(bins >= 1 && bins <= 4096, "soft_hist: bins=%d (need 1..4096)", bins);
   int64_t shp[4] = {n, h, w, (int64_t)c * bins};
-  DL_TRY(dl_alloc(shp, 4, v.dev, out));
+  DL_TRY(dl_alloc(shp, 4, v.dev, (cudaStream_t)stream, out));
   DL_RUN(out, shdr_soft_hist_f32(v.p, (float*)(*out)->dl_tensor.data, n, h, w, c, bins, pool_k, c * bins, 0, stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }
 
@@ -296,8 +342,9 @@ extern "C" int shdr_dl_invcrf_build(const struct DLManagedTensor* w, int monoton
   DL_TRY(dl_view(w, "invcrf_build", &v));
   SHDR_REQUIRE(v.ndim == 2 && v.shape[1] == SHDR_EMOR_NCOMP, "invcrf_build: w must be [b,%d]", SHDR_EMOR_NCOMP);
   int64_t shp[2] = {v.shape[0], SHDR_EMOR_SAMPLES};
-  DL_TRY(dl_alloc(shp, 2, v.dev, out));
+  DL_TRY(dl_alloc(shp, 2, v.dev, (cudaStream_t)stream, out));
   DL_RUN(out, shdr_invcrf_build_f32(v.p, (float*)(*out)->dl_tensor.data, (int)v.shape[0], monotone, stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }
 
@@ -306,8 +353,9 @@ extern "C" int shdr_dl_increase(const struct DLManagedTensor* rf, void* stream, 
   DL_TRY(dl_view(rf, "increase", &v));
   SHDR_REQUIRE(v.ndim == 2, "increase: rf must be [b,k]");
   int64_t shp[2] = {v.shape[0], v.shape[1]};
-  DL_TRY(dl_alloc(shp, 2, v.dev, out));
+  DL_TRY(dl_alloc(shp, 2, v.dev, (cudaStream_t)stream, out));
   DL_RUN(out, shdr_increase_f32(v.p, (float*)(*out)->dl_tensor.data, (int)v.shape[0], (int)v.shape[1], stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }
 
@@ -323,8 +371,9 @@ extern "C" int shdr_dl_apply_rf(const struct DLManagedTensor* x, const struct DL
   SHDR_REQUIRE(vr.shape[1] >= 1 && vr.shape[1] <= 0x7fffffff, "apply_rf: k out of range");
   const int b = (int)vx.shape[0];
   const long long per = b > 0 ? vx.numel / b : 0;
-  DL_TRY(dl_alloc(vx.shape, vx.ndim, vx.dev, out));
+  DL_TRY(dl_alloc(vx.shape, vx.ndim, vx.dev, (cudaStream_t)stream, out));
   DL_RUN(out, shdr_apply_rf_f32(vx.p, vr.p, (float*)(*out)->dl_tensor.data, b, per, (int)vr.shape[1], stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }
 

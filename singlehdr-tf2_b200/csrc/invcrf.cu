@@ -183,11 +183,6 @@ k_apply_rf(const float* __restrict__ x, const float* __restrict__ rf, float* __r
   const long long item = blockIdx.x / chunks_per_item;
   const int chunk = blockIdx.x - (int)(item * chunks_per_item);
   const float* r = rf + item * k;
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent of k_curve
-  if (SMEM) {
-    for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
-    __syncthreads();
-  }
   const float km1 = (float)(k - 1);
   const int kmax = k - 1;
   const long long e0 = (long long)chunk * elems_per_chunk;
@@ -200,16 +195,24 @@ k_apply_rf(const float* __restrict__ x, const float* __restrict__ rf, float* __r
     const float4* x4 = reinterpret_cast<const float4*>(xi);
     float4* y4 = reinterpret_cast<float4*>(yi);
     const long long v1 = e1 >> 2;
-    for (long long v = (e0 >> 2) + tid; v < v1; v += APPLY_THREADS * APPLY_UNROLL) {
-      float4 in[APPLY_UNROLL];
+    long long v = (e0 >> 2) + tid;
+    // x does not depend on the curve kernel: when this grid runs as a programmatic dependent of k_curve
+    // (shdr_linearize_f32) the first batch of loads is in flight while k_curve finishes
+    float4 in[APPLY_UNROLL];
+#pragma unroll
+    for (int u = 0; u < APPLY_UNROLL; ++u) {
+      const long long vv = v + u * APPLY_THREADS;
+      if (vv < v1) in[u] = ld_stream4(x4 + vv);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
+    if (SMEM) {
+      for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
+      __syncthreads();
+    }
+    for (; v < v1; v += APPLY_THREADS * APPLY_UNROLL) {
 #pragma unroll
       for (int u = 0; u < APPLY_UNROLL; ++u) {
-        long long vv = v + u * APPLY_THREADS;
-        if (vv < v1) in[u] = ld_stream4(x4 + vv);
-      }
-#pragma unroll
-      for (int u = 0; u < APPLY_UNROLL; ++u) {
-        long long vv = v + u * APPLY_THREADS;
+        const long long vv = v + u * APPLY_THREADS;
         if (vv < v1) {
           float4 o;
           o.x = lerp_lookup<SMEM>(in[u].x, tab, r, km1, kmax);
@@ -219,11 +222,145 @@ k_apply_rf(const float* __restrict__ x, const float* __restrict__ rf, float* __r
           st_stream4(y4 + vv, o);
         }
       }
+      const long long vn = v + APPLY_THREADS * APPLY_UNROLL;
+#pragma unroll
+      for (int u = 0; u < APPLY_UNROLL; ++u) {
+        const long long vv = vn + u * APPLY_THREADS;
+        if (vv < v1) in[u] = ld_stream4(x4 + vv);
+      }
     }
   } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (SMEM) {
+      for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
+      __syncthreads();
+    }
     for (long long e = e0 + tid; e < e1; e += APPLY_THREADS)
       yi[e] = lerp_lookup<SMEM>(__ldg(xi + e), tab, r, km1, kmax);
   }
+}
+
+// ---- the steps either side of apply_rf in the inference graph, fused:
+//   c = clip_by_value(x, 0, 1)                                        test_real_refinement.py:91
+//   y = apply_rf(c, rf)                                               :95
+//   alpha = min(1, max(0, max_c(y) - 1 + thr) / thr) tiled x 3        :98-101
+// One thread handles whole RGB pixels (4 at a time when vectorised: 12 floats = 3 x 128 bit).
+__device__ __forceinline__ float alpha_of(float a, float b, float c, float thr) {
+  float m = fmaxf(fmaxf(a, b), c);                          // reduce_max over the channel axis
+  float t = __fadd_rn(__fsub_rn(m, 1.0f), thr);             // alpha - 1.0 + THRESHOLD
+  t = __fdiv_rn(fmaxf(0.0f, t), thr);                       // maximum(0.0, .) / THRESHOLD
+  return fminf(1.0f, t);
+}
+__device__ __forceinline__ float clip01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+template <bool SMEM, bool VEC>
+__global__ void __launch_bounds__(APPLY_THREADS)
+k_apply_rf_px(const float* __restrict__ x, const float* __restrict__ rf, float* __restrict__ y,
+              float* __restrict__ clipped, float* __restrict__ alpha, long long px_per_item, int k,
+              int chunks_per_item, long long px_per_chunk, int clip, float thr) {
+  extern __shared__ float2 tab[];
+  const int tid = threadIdx.x;
+  const long long item = blockIdx.x / chunks_per_item;
+  const int chunk = blockIdx.x - (int)(item * chunks_per_item);
+  const float* r = rf + item * k;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (SMEM) {
+    for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
+    __syncthreads();
+  }
+  const float km1 = (float)(k - 1);
+  const int kmax = k - 1;
+  const long long p0 = (long long)chunk * px_per_chunk;
+  const long long p1 = min(p0 + px_per_chunk, px_per_item);
+  const long long base = item * px_per_item * 3;
+  if (VEC) {
+    const float4* x4 = reinterpret_cast<const float4*>(x + base);
+    float4* y4 = reinterpret_cast<float4*>(y + base);
+    float4* c4 = clipped ? reinterpret_cast<float4*>(clipped + base) : nullptr;
+    float4* a4 = alpha ? reinterpret_cast<float4*>(alpha + base) : nullptr;
+    for (long long g = (p0 >> 2) + tid; g < (p1 >> 2); g += APPLY_THREADS) {   // group of 4 pixels = 3 float4
+      float v[12], o[12];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 t = ld_stream4(x4 + g * 3 + q);
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        if (clip) v[i] = clip01(v[i]);
+        o[i] = lerp_lookup<SMEM>(v[i], tab, r, km1, kmax);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        st_stream4(y4 + g * 3 + q, make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+        if (c4) st_stream4(c4 + g * 3 + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      }
+      if (a4) {
+        float a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = alpha_of(o[3 * i], o[3 * i + 1], o[3 * i + 2], thr);
+        st_stream4(a4 + g * 3 + 0, make_float4(a[0], a[0], a[0], a[1]));
+        st_stream4(a4 + g * 3 + 1, make_float4(a[1], a[1], a[2], a[2]));
+        st_stream4(a4 + g * 3 + 2, make_float4(a[2], a[3], a[3], a[3]));
+      }
+    }
+  } else {
+    for (long long px = p0 + tid; px < p1; px += APPLY_THREADS) {
+      float o[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = __ldg(x + base + px * 3 + c);
+        if (clip) v = clip01(v);
+        if (clipped) clipped[base + px * 3 + c] = v;
+        o[c] = lerp_lookup<SMEM>(v, tab, r, km1, kmax);
+        y[base + px * 3 + c] = o[c];
+      }
+      if (alpha) {
+        const float a = alpha_of(o[0], o[1], o[2], thr);
+        alpha[base + px * 3] = a; alpha[base + px * 3 + 1] = a; alpha[base + px * 3 + 2] = a;
+      }
+    }
+  }
+}
+
+template <bool SMEM, bool VEC>
+static int launch_apply_px_t(const float* x, const float* rf, float* y, float* clipped, float* alpha, int b,
+                             long long npx, int k, int clip, float thr, cudaStream_t st, int dev, bool pdl) {
+  const long long quantum = 4LL * APPLY_THREADS;            // pixels: every thread one group of 4
+  long long per_chunk = quantum * 8;
+  const long long want = (long long)sm_count(dev) * 8;
+  while (per_chunk > quantum && (long long)b * ((npx + per_chunk - 1) / per_chunk) < want) per_chunk >>= 1;
+  const long long chunks = (npx + per_chunk - 1) / per_chunk;
+  const long long grid = (long long)b * chunks;
+  SHDR_REQUIRE(grid > 0 && grid <= 0x7fffffffLL, "apply_rf_ex: grid of %lld CTAs is out of range", grid);
+  const size_t smem = SMEM ? (size_t)k * sizeof(float2) : 0;
+  if (smem > 48 * 1024)
+    SHDR_CUDA(cudaFuncSetAttribute(k_apply_rf_px<SMEM, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(APPLY_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SHDR_CUDA(cudaLaunchKernelEx(&cfg, k_apply_rf_px<SMEM, VEC>, x, rf, y, clipped, alpha, npx, k, (int)chunks, per_chunk,
+                               clip, thr));
+  SHDR_LAUNCH_CHECK("k_apply_rf_px");
+  return SHDR_OK;
+}
+
+static int launch_apply_px(const float* x, const float* rf, float* y, float* clipped, float* alpha, int b,
+                           long long npx, int k, int clip, float thr, cudaStream_t st, int dev, bool pdl = false) {
+  const bool vec = (npx % 4 == 0) && aligned16(x) && aligned16(y) && (!clipped || aligned16(clipped)) &&
+                   (!alpha || aligned16(alpha));
+  const bool smem = (size_t)k * sizeof(float2) <= 200 * 1024;
+  if (smem) return vec ? launch_apply_px_t<true, true>(x, rf, y, clipped, alpha, b, npx, k, clip, thr, st, dev, pdl)
+                       : launch_apply_px_t<true, false>(x, rf, y, clipped, alpha, b, npx, k, clip, thr, st, dev, pdl);
+  return vec ? launch_apply_px_t<false, true>(x, rf, y, clipped, alpha, b, npx, k, clip, thr, st, dev, pdl)
+             : launch_apply_px_t<false, false>(x, rf, y, clipped, alpha, b, npx, k, clip, thr, st, dev, pdl);
 }
 
 template <bool SMEM, bool VEC>
@@ -308,4 +445,31 @@ extern "C" int shdr_linearize_f32(const float* x, const float* w, float* y, floa
   int rc = launch_curve(w, nullptr, curve_out, b, SHDR_EMOR_SAMPLES, 1, (cudaStream_t)stream, g.dev);
   if (rc != SHDR_OK || elems_per_item == 0) return rc;
   return launch_apply(x, curve_out, y, b, elems_per_item, SHDR_EMOR_SAMPLES, (cudaStream_t)stream, g.dev, true);
+}
+
+extern "C" int shdr_apply_rf_ex_f32(const float* x, const float* rf, float* y, float* clipped_out, float* alpha_out,
+                                    int b, long long pixels_per_item, int k, int clip, float thr, void* stream) {
+  SHDR_REQUIRE(b >= 0 && pixels_per_item >= 0, "apply_rf_ex: b=%d pixels_per_item=%lld", b, pixels_per_item);
+  SHDR_REQUIRE(k >= 1, "apply_rf_ex: k=%d", k);
+  SHDR_REQUIRE(!alpha_out || thr > 0.0f, "apply_rf_ex: the alpha mask needs thr > 0 (got %g)", (double)thr);
+  if (b == 0 || pixels_per_item == 0) return SHDR_OK;
+  SHDR_REQUIRE(x && rf && y, "apply_rf_ex: NULL pointer");
+  DeviceGuard g(y);
+  if (g.status != SHDR_OK) return g.status;
+  return launch_apply_px(x, rf, y, clipped_out, alpha_out, b, pixels_per_item, k, clip, thr, (cudaStream_t)stream, g.dev);
+}
+
+extern "C" int shdr_linearize_ex_f32(const float* x, const float* w, float* y, float* curve_out, float* clipped_out,
+                                     float* alpha_out, int b, long long pixels_per_item, int clip, float thr,
+                                     void* stream) {
+  SHDR_REQUIRE(b >= 0 && pixels_per_item >= 0, "linearize_ex: b=%d pixels_per_item=%lld", b, pixels_per_item);
+  SHDR_REQUIRE(!alpha_out || thr > 0.0f, "linearize_ex: the alpha mask needs thr > 0 (got %g)", (double)thr);
+  if (b == 0) return SHDR_OK;
+  SHDR_REQUIRE(x && w && y && curve_out, "linearize_ex: NULL pointer");
+  DeviceGuard g(y);
+  if (g.status != SHDR_OK) return g.status;
+  int rc = launch_curve(w, nullptr, curve_out, b, SHDR_EMOR_SAMPLES, 1, (cudaStream_t)stream, g.dev);
+  if (rc != SHDR_OK || pixels_per_item == 0) return rc;
+  return launch_apply_px(x, curve_out, y, clipped_out, alpha_out, b, pixels_per_item, SHDR_EMOR_SAMPLES, clip, thr,
+                         (cudaStream_t)stream, g.dev, true);
 }

@@ -79,6 +79,7 @@ class DeviceArray:
         if a.size:
             N.check(N.lib.shdr_h2d(d.ptr, a.ctypes.data, a.nbytes, device, stream))
             N.check(N.lib.shdr_stream_sync(stream, device))
+        d.mark_ready(stream)
         return d
 
     # -- properties
@@ -98,6 +99,8 @@ class DeviceArray:
         self._alive()
         out = np.empty(self.shape, np.float32)
         if out.size:
+            # the copy stream waits for the producing kernel (whatever stream it ran on)
+            N.check(N.lib.shdr_dl_wait_ready(self._m, getattr(stream, "handle", stream), 0))
             N.check(N.lib.shdr_d2h(out.ctypes.data, self.ptr, out.nbytes, self.device, stream))
             N.check(N.lib.shdr_stream_sync(stream, self.device))
         return out
@@ -106,12 +109,24 @@ class DeviceArray:
     def __dlpack_device__(self):
         return (2, self.device)        # kDLCUDA
 
-    def __dlpack__(self, stream=None, **_unused):
+    def mark_ready(self, stream=None):
+        """Record that the work just enqueued on ``stream`` produces this tensor (the ``shdr_dl_*`` ops do it
+        themselves); ``__dlpack__`` / ``numpy`` then wait for exactly that work instead of the whole device."""
         self._alive()
-        if stream != -1:
-            # the producing kernel may have been enqueued on any stream the caller gave the op:
-            # make it visible to whichever stream the consumer uses (-1 = "do not synchronise")
-            N.check(N.lib.shdr_sync(self.device))
+        N.check(N.lib.shdr_dl_mark_ready(self._m, getattr(stream, "handle", stream)))
+        return self
+
+    def __dlpack__(self, stream=None, **_unused):
+        """DLPack producer protocol.  ``stream``: the consumer's CUDA stream (an integer handle; 1 and 2 are the
+        legacy / per-thread default streams) -> that stream is made to wait for the producing kernel; ``None`` (what
+        ``from_dlpack(capsule)`` callers such as TF effectively give) -> the HOST waits for the producing kernel only
+        (an event, not a device-wide synchronise); ``-1`` -> no synchronisation."""
+        self._alive()
+        if stream is None:
+            N.check(N.lib.shdr_dl_wait_ready(self._m, None, 1))
+        elif stream != -1:
+            h = None if stream in (0, 1) else stream          # 1 = legacy default stream; 2 = per-thread default
+            N.check(N.lib.shdr_dl_wait_ready(self._m, h, 0))
         cap = _pyapi.PyCapsule_New(self._m, _DLTENSOR, _CAPSULE_DTOR)
         self._m = None
         return cap

@@ -37,11 +37,32 @@ def _stream(stream):
 
 
 def _run_dl(fn, ins, *args, stream=None):
-    """Call a shdr_dl_* entry: borrowed inputs first, then scalar args, stream, &out."""
+    """Call a shdr_dl_* entry: borrowed inputs first, then scalar args, stream, &out.
+
+    Stream contract: the kernel is enqueued on ``stream`` (``None`` = the legacy default stream), so the INPUTS must
+    already be ordered before that stream -- true for producers on the legacy stream (torch by default) and for
+    :class:`DeviceArray` inputs, whose ready event is waited for here; a framework with private non-blocking streams
+    (TensorFlow) must synchronise first, which ``tf_adapter`` does.  The borrowed capsules are released when this
+    returns, i.e. possibly before the kernel has run: callers that may free the inputs right away keep them alive
+    until the output is ready (``tf_adapter`` holds them until its host-side wait)."""
     borrowed = [Borrowed(x) for x in ins]
+    sh = _stream(stream)
+    for b, x in zip(borrowed, ins):
+        if isinstance(x, DeviceArray):
+            N.check(N.lib.shdr_dl_wait_ready(b.managed, sh, 0))
     out = C.c_void_p()
-    N.check(fn(*[b.managed for b in borrowed], *args, _stream(stream), C.byref(out)))
+    N.check(fn(*[b.managed for b in borrowed], *args, sh, C.byref(out)))
     return DeviceArray(out.value)
+
+
+def _dev_inputs(stream, *xs):
+    """Borrow inputs for a raw-pointer entry point; DeviceArray inputs make ``stream`` wait for their producer."""
+    bs = [Borrowed(x) for x in xs]
+    sh = _stream(stream)
+    for b, x in zip(bs, xs):
+        if isinstance(x, DeviceArray):
+            N.check(N.lib.shdr_dl_wait_ready(b.managed, sh, 0))
+    return bs
 
 
 # --------------------------------------------------------------------------- front end
@@ -67,17 +88,18 @@ def frontend(img, pool=False, stream=None):
 
 def hist_multi(img, pool=False, stream=None):
     """``concat([hist4, hist8, hist16], -1)`` -> ``[b,h,w,84]`` in one launch."""
-    b = Borrowed(img)
+    (b,) = _dev_inputs(stream, img)
     if len(b.shape) != 4 or b.shape[3] != 3:
         raise ValueError(f"hist_multi: img must be [n,h,w,3], got {b.shape}")
     n, h, w, _ = b.shape
     out = DeviceArray.empty((n, h, w, N.HIST_CH), b.device)
     N.check(N.lib.shdr_hist_multi_f32(b.ptr, out.ptr, n, h, w, POOL_K if pool else 0, _stream(stream)))
-    return out
+    return out.mark_ready(stream)
 
 
 # --------------------------------------------------------------------------- EMoR table
 _table_cache = {}
+_registered_key = None            # the table file currently installed in libshdr (by parse_invemor)
 
 
 def _read_block(lines, tag):
@@ -106,8 +128,10 @@ def parse_invemor(path="invemor.txt", register=True):
         g0 = _read_block(lines, "g0 =")
         hinv = np.stack([_read_block(lines, f"hinv({i + 1})=") for i in range(N.EMOR_NCOMP)], axis=-1)
         hit = _table_cache[key] = (b, g0, np.ascontiguousarray(hinv))
-    if register:
+    global _registered_key
+    if register and _registered_key != key:      # the reference re-parses on every call; re-register only on a change
         set_emor_table(hit[1], hit[2])
+        _registered_key = key
     return hit
 
 
@@ -117,6 +141,8 @@ def set_emor_table(g0, hinv):
     hinv = np.ascontiguousarray(hinv, dtype=np.float32)
     if g0.shape != (N.EMOR_SAMPLES,) or hinv.shape != (N.EMOR_SAMPLES, N.EMOR_NCOMP):
         raise ValueError(f"EMoR table must be g0[1024], hinv[1024,11]; got {g0.shape}, {hinv.shape}")
+    global _registered_key
+    _registered_key = None                       # an explicit table overrides whatever parse_invemor installed
     N.check(N.lib.shdr_set_emor_table(g0.ctypes.data, hinv.ctypes.data, N.EMOR_SAMPLES, N.EMOR_NCOMP))
 
 
@@ -144,7 +170,7 @@ def apply_rf(x, rf, stream=None):
 def linearize(x, invcrf_pca_w, stream=None):
     """``apply_rf(x, _increase(invcrf_pca_w_2_invcrf(w)))`` back to back on one stream
     (linearization_net.py:325-328 + test_real_refinement.py:95).  Returns ``(y, curve)``."""
-    bx, bw = Borrowed(x), Borrowed(invcrf_pca_w)
+    bx, bw = _dev_inputs(stream, x, invcrf_pca_w)
     if len(bw.shape) != 2 or bw.shape[1] != N.EMOR_NCOMP or not bx.shape or bx.shape[0] != bw.shape[0]:
         raise ValueError(f"linearize: x {bx.shape} / w {bw.shape} mismatch (w must be [b,11])")
     b = bx.shape[0]
@@ -152,7 +178,109 @@ def linearize(x, invcrf_pca_w, stream=None):
     y = DeviceArray.empty(bx.shape, bx.device)
     curve = DeviceArray.empty((b, N.EMOR_SAMPLES), bx.device)
     N.check(N.lib.shdr_linearize_f32(bx.ptr, bw.ptr, y.ptr, curve.ptr, b, per, _stream(stream)))
-    return y, curve
+    return y.mark_ready(stream), curve.mark_ready(stream)
+
+
+def linearize_ex(x, invcrf_pca_w=None, rf=None, clip=True, alpha_threshold=None, want_clipped=False, stream=None):
+    """The inference graph around ``apply_rf`` in ONE pass over the image (test_real_refinement.py:91-101)::
+
+        C_pred = tf.clip_by_value(pred_deq, 0, 1)                       # clip=True
+        B_pred = tf_utils.apply_rf(C_pred, pred_invcrf)
+        alpha  = min(1, max(0, reduce_max(B_pred, 3) - 1 + thr) / thr)  # alpha_threshold=thr, tiled to 3 channels
+
+    ``x`` is ``[b,h,w,3]``.  The curve comes either from the PCA weights ``invcrf_pca_w [b,11]`` (build + ``_increase``
+    fused in front, as :func:`linearize`) or from ``rf [b,k]``.  Returns a dict with ``y`` (B_pred) and, when
+    requested, ``clipped`` (C_pred), ``alpha`` ``[b,h,w,3]`` and ``curve``."""
+    if (invcrf_pca_w is None) == (rf is None):
+        raise ValueError("linearize_ex: give exactly one of invcrf_pca_w and rf")
+    bx, bc = _dev_inputs(stream, x, invcrf_pca_w if rf is None else rf)
+    if len(bx.shape) < 2 or bx.shape[-1] != 3 or len(bc.shape) != 2 or bc.shape[0] != bx.shape[0]:
+        raise ValueError(f"linearize_ex: x {bx.shape} must be [b,...,3] and the curve input [b,*], got {bc.shape}")
+    if alpha_threshold is not None and not alpha_threshold > 0:
+        raise ValueError("linearize_ex: alpha_threshold must be > 0")
+    b = bx.shape[0]
+    npx = int(np.prod(bx.shape[1:-1], dtype=np.int64))
+    sh = _stream(stream)
+    out = {"y": DeviceArray.empty(bx.shape, bx.device)}
+    cl = DeviceArray.empty(bx.shape, bx.device) if want_clipped else None
+    al = DeviceArray.empty(bx.shape, bx.device) if alpha_threshold is not None else None
+    thr = float(alpha_threshold) if alpha_threshold is not None else 1.0
+    if rf is None:
+        if bc.shape[1] != N.EMOR_NCOMP:
+            raise ValueError(f"linearize_ex: invcrf_pca_w must be [b,11], got {bc.shape}")
+        out["curve"] = DeviceArray.empty((b, N.EMOR_SAMPLES), bx.device)
+        N.check(N.lib.shdr_linearize_ex_f32(bx.ptr, bc.ptr, out["y"].ptr, out["curve"].ptr, cl.ptr if cl else None,
+                                            al.ptr if al else None, b, npx, 1 if clip else 0, thr, sh))
+    else:
+        N.check(N.lib.shdr_apply_rf_ex_f32(bx.ptr, bc.ptr, out["y"].ptr, cl.ptr if cl else None,
+                                           al.ptr if al else None, b, npx, bc.shape[1], 1 if clip else 0, thr, sh))
+    if cl is not None:
+        out["clipped"] = cl
+    if al is not None:
+        out["alpha"] = al
+    for v in out.values():
+        v.mark_ready(stream)
+    return out
+
+
+# --------------------------------------------------------------------------- gradients (training steps)
+def apply_rf_bwd(x, rf, gy, need_gx=True, need_grf=True, stream=None):
+    """Gradient of :func:`apply_rf`: returns ``(gx, grf)`` (``None`` for the one not asked for).
+    ``gx = gy (k-1) (rf[i1] - rf[i0])``; ``grf[b]`` = scatter-add of ``gy (y1-y)`` at ``i0`` and ``gy (y-y0)`` at ``i1``
+    -- what TF's autodiff gives for tf_utils.py:54-105 (train.py:186-194)."""
+    bx, br, bg = _dev_inputs(stream, x, rf, gy)
+    if len(br.shape) != 2 or not bx.shape or bx.shape[0] != br.shape[0] or tuple(bg.shape) != tuple(bx.shape):
+        raise ValueError(f"apply_rf_bwd: x {bx.shape}, rf {br.shape}, gy {bg.shape} mismatch")
+    b, k = br.shape
+    per = int(np.prod(bx.shape[1:], dtype=np.int64))
+    gx = DeviceArray.empty(bx.shape, bx.device) if need_gx else None
+    grf = DeviceArray.empty((b, k), bx.device) if need_grf else None
+    N.check(N.lib.shdr_apply_rf_bwd_f32(bx.ptr, br.ptr, bg.ptr, gx.ptr if gx else None, grf.ptr if grf else None,
+                                        b, per, k, _stream(stream)))
+    return (gx.mark_ready(stream) if gx else None), (grf.mark_ready(stream) if grf else None)
+
+
+def _increase_bwd(rf, gout, stream=None):
+    """Gradient of :func:`_increase` w.r.t. ``rf [b,k]`` (linearization_net.py:368-392)."""
+    br, bg = _dev_inputs(stream, rf, gout)
+    if len(br.shape) != 2 or tuple(bg.shape) != tuple(br.shape):
+        raise ValueError(f"_increase_bwd: rf {br.shape} / gout {bg.shape} mismatch")
+    out = DeviceArray.empty(br.shape, br.device)
+    N.check(N.lib.shdr_increase_bwd_f32(br.ptr, bg.ptr, out.ptr, br.shape[0], br.shape[1], _stream(stream)))
+    return out.mark_ready(stream)
+
+
+def invcrf_build_bwd(invcrf_pca_w, gcurve, monotone=False, stream=None):
+    """Gradient of :func:`invcrf_pca_w_2_invcrf` (``monotone=False``) or :func:`invcrf_build` (PCA + ``_increase``)
+    w.r.t. ``w [b,11]``; ``gcurve`` is ``[b,1024]``."""
+    bw, bg = _dev_inputs(stream, invcrf_pca_w, gcurve)
+    if len(bw.shape) != 2 or bw.shape[1] != N.EMOR_NCOMP or tuple(bg.shape) != (bw.shape[0], N.EMOR_SAMPLES):
+        raise ValueError(f"invcrf_build_bwd: w {bw.shape} / gcurve {bg.shape} mismatch")
+    out = DeviceArray.empty(bw.shape, bw.device)
+    N.check(N.lib.shdr_invcrf_build_bwd_f32(bw.ptr, bg.ptr, out.ptr, bw.shape[0], 1 if monotone else 0, _stream(stream)))
+    return out.mark_ready(stream)
+
+
+def frontend_bwd(img, gfeat, stream=None):
+    """Gradient of :func:`frontend` (un-pooled) w.r.t. ``img``: ``gfeat [n,h,w,93] -> [n,h,w,3]``."""
+    bi, bg = _dev_inputs(stream, img, gfeat)
+    if len(bi.shape) != 4 or bi.shape[3] != 3 or tuple(bg.shape) != tuple(bi.shape[:3]) + (N.FRONTEND_CH,):
+        raise ValueError(f"frontend_bwd: img {bi.shape} / gfeat {bg.shape} mismatch")
+    n, h, w, _ = bi.shape
+    out = DeviceArray.empty(bi.shape, bi.device)
+    N.check(N.lib.shdr_frontend_bwd_f32(bi.ptr, bg.ptr, out.ptr, n, h, w, _stream(stream)))
+    return out.mark_ready(stream)
+
+
+def histogram_layer_bwd(img, ghist, max_bin, stream=None):
+    """Gradient of :func:`histogram_layer` (un-pooled) w.r.t. ``img``."""
+    bi, bg = _dev_inputs(stream, img, ghist)
+    if len(bi.shape) != 4 or tuple(bg.shape) != tuple(bi.shape[:3]) + (bi.shape[3] * int(max_bin),):
+        raise ValueError(f"histogram_layer_bwd: img {bi.shape} / ghist {bg.shape} mismatch")
+    n, h, w, c = bi.shape
+    out = DeviceArray.empty(bi.shape, bi.device)
+    N.check(N.lib.shdr_soft_hist_bwd_f32(bi.ptr, bg.ptr, out.ptr, n, h, w, c, int(max_bin), _stream(stream)))
+    return out.mark_ready(stream)
 
 
 # --------------------------------------------------------------------------- reference-shaped classes

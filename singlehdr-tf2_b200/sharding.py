@@ -3,10 +3,10 @@
 Every batch item is independent in every stage (front end: per-image stencil,
 linearization_net.py:312-350; curve: per batch row, :231-253, 369-392; apply_rf uses
 rf[b] for image b only, tf_utils.py:61-68), so ranks get disjoint item ranges and the
-hot path needs NO collective.  The only exchange offered is an optional gather of the
-small outputs (curves) for a caller that wants them in one place; it goes through
-whatever ``torch.distributed`` process group the launcher created (NCCL on GPUs, gloo
-in the CPU tests) and is off the timed path.
+hot path needs NO collective.  An optional gather of the small outputs (curves) for a
+caller that wants them in one place is launcher plumbing, not product code: see
+``tools/dist_gather.py`` (``torch.distributed`` all-gather: NCCL on GPUs, gloo in the CPU
+tests), which this package does not import.
 """
 from __future__ import annotations
 
@@ -34,24 +34,3 @@ def row_tiles(h: int, parts: int, halo_before: int, halo_after: int):
         y0, y1 = shard_range(h, parts, r)
         tiles.append((y0, y1, max(0, y0 - halo_before), min(h, y1 + halo_after)))
     return tiles
-
-
-def gather_to_all(local, group=None):
-    """All-gather equally-shaped per-rank tensors (e.g. curves ``[b_local,1024]``) with
-    ``torch.distributed`` -- the optional NCCL gather of outputs.  ``local`` is a torch tensor
-    (CUDA for NCCL, CPU for gloo).  Ragged shards are padded to the largest and trimmed."""
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group)
-    n_local = torch.tensor([local.shape[0]], device=local.device, dtype=torch.int64)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
-    m = max(counts)
-    pad = local
-    if local.shape[0] < m:
-        pad = torch.cat([local, local.new_zeros((m - local.shape[0],) + tuple(local.shape[1:]))], 0)
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad.contiguous(), group=group)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)], 0)

@@ -30,7 +30,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, s), f"{s} declared in include/shdr.h but not exported"
         assert s in _native.SIGNATURES, f"{s} has no ctypes signature in _native.py"
     assert set(_native.SIGNATURES) == set(syms)
-    assert _native.lib.shdr_version() == 100
+    assert _native.lib.shdr_version() == 200
     assert shdr.launch_count() >= 0
 
 

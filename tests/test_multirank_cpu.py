@@ -31,7 +31,8 @@ def _worker(rank, world, port, n_items, out_q):
     a, b = shdr.shard_range(n_items, world, rank)
     local = oracle.increase(oracle.invcrf_pca_w_2_invcrf(w[a:b], z["g0"], z["hinv"])) if b > a \
         else np.zeros((0, 1024), np.float32)
-    full = shdr.gather_to_all(torch.from_numpy(local))
+    from tools.dist_gather import gather_to_all
+    full = gather_to_all(torch.from_numpy(local))
     dist.barrier()
     if rank == 0:
         out_q.put(full.numpy())
