@@ -50,7 +50,9 @@ k_apply_rf_bwd(const float* __restrict__ x, const float* __restrict__ rf, const 
     const float y1 = __fadd_rn(y0, 1.0f);
     const int i0 = min(max(__float2int_rz(y0), 0), kmax);
     const int i1 = min(max(__float2int_rz(y1), 0), kmax);
-    if (NEED_GX) gxi[e] = km1 * (g * tab[i1] - g * tab[i0]);
+    // difference first: neighbouring curve samples are close, so their difference is (nearly) exact in fp32, while
+    // g*rf[i1] - g*rf[i0] would amplify the products' rounding by k - 1
+    if (NEED_GX) gxi[e] = km1 * (g * (tab[i1] - tab[i0]));
     if (NEED_GRF) {
       atomicAdd(acc + i0, g * __fsub_rn(y1, y));
       atomicAdd(acc + i1, g * __fsub_rn(y, y0));

@@ -145,6 +145,10 @@ class Borrowed:
 
     def __init__(self, obj):
         self._keep = obj
+        if isinstance(obj, Borrowed):                 # already borrowed (tf_adapter holds inputs across a call)
+            self.managed = obj.managed
+            self.ptr, self.shape, self.device, self.device_type = obj.ptr, obj.shape, obj.device, obj.device_type
+            return
         if isinstance(obj, DeviceArray):
             obj._alive()
             self.managed = obj._m

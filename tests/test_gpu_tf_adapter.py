@@ -18,6 +18,9 @@ import oracle
 pytestmark = pytest.mark.gpu
 
 
+SUMMARIES = []
+
+
 class FakeTFTensor:
     """Looks like a TF eager tensor to the adapter: no __dlpack__, module name starts with 'tensorflow'."""
     __module__ = "tensorflow.python.framework.ops"
@@ -29,6 +32,9 @@ class FakeTFTensor:
     def numpy(self):
         return self._t.cpu().numpy()
 
+    def __getitem__(self, idx):
+        return FakeTFTensor(self._t[idx].contiguous())
+
 
 def _install_fake_tf():
     import torch
@@ -36,6 +42,17 @@ def _install_fake_tf():
     tf.float32 = "float32"
     tf.executing_eagerly = lambda: True
     tf.py_function = lambda fn, args, dtype: fn(*args)
+    tf.cast = lambda x, dtype: x
+    tf.summary = types.SimpleNamespace(image=lambda name, t: SUMMARIES.append((name, t.shape)))
+
+    def custom_gradient(f):
+        """records the gradient function on the output, the way a GradientTape would hold it"""
+        def wrapper(*xs):
+            y, grad = f(*xs)
+            y._grad_fn = grad
+            return y
+        return wrapper
+    tf.custom_gradient = custom_gradient
     dl = types.SimpleNamespace(
         to_dlpack=lambda x: torch.utils.dlpack.to_dlpack(x._t),
         from_dlpack=lambda cap: FakeTFTensor(torch.utils.dlpack.from_dlpack(cap)))
@@ -64,6 +81,9 @@ def test_patch_reference_modules(shdr_gpu, emor, tmp_path, monkeypatch):
         lin = types.ModuleType("linearization_net")
 
         class model:            # noqa: N801  (reference spelling)
+            def call(self, img, training="training"):
+                raise AssertionError("stock TF path must have been replaced")
+
             def histogram_layer(self, img, max_bin):
                 raise AssertionError("stock TF path must have been replaced")
 
@@ -102,6 +122,53 @@ def test_patch_reference_modules(shdr_gpu, emor, tmp_path, monkeypatch):
         lin_img = tfu.apply_rf(t_img, curve)
         assert lin_img.shape == img.shape
         assert np.abs(lin_img.numpy() - oracle.apply_rf(img, ref_curve)).max() <= 1e-5
+
+        # ---- gradients ride on tf.custom_gradient (the training steps differentiate through these ops)
+        gy = rng.normal(size=img.shape).astype(np.float32)
+        gx, grf = lin_img._grad_fn(FakeTFTensor(torch.from_numpy(gy).cuda()))
+        rx, rrf = oracle.apply_rf_grad(img, curve.numpy(), gy)
+        assert np.abs(gx.numpy() - rx).max() <= 2e-5 * np.abs(rx).max()
+        assert np.abs(grf.numpy() - rrf).max() <= 1e-4 * np.abs(rrf).max()
+        gc = rng.normal(size=(2, 1024)).astype(np.float32)
+        g_inc = curve._grad_fn(FakeTFTensor(torch.from_numpy(gc).cuda()))
+        want = oracle.increase_grad(pca.numpy(), gc)
+        assert np.abs(g_inc.numpy() - want).max() <= 5e-5 * np.abs(want).max()
+        g_w = pca._grad_fn(FakeTFTensor(torch.from_numpy(gc).cuda()))
+        want = oracle.invcrf_pca_grad(gc, hinv)
+        assert np.abs(g_w.numpy() - want).max() <= 5e-5 * np.abs(want).max()
+        gf = rng.normal(size=(2, 24, 40, 93)).astype(np.float32)
+        g_img = feat._grad_fn(FakeTFTensor(torch.from_numpy(gf).cuda()))
+        want = oracle.frontend_grad(img, gf)
+        assert np.abs(g_img.numpy() - want).max() <= 2e-5 * np.abs(want).max()
+        gh = rng.normal(size=(2, 24, 40, 24)).astype(np.float32)
+        g_img = hist._grad_fn(FakeTFTensor(torch.from_numpy(gh).cuda()))
+        want = oracle.histogram_layer_grad(img, gh, 8)
+        assert np.abs(g_img.numpy() - want).max() <= 2e-5 * np.abs(want).max()
+
+        # ---- model.call itself is replaced: fused front end -> stock sub-networks -> native _increase
+        proj = rng.normal(0, 0.05, (93, 11)).astype(np.float32)
+        seen = {}
+
+        def crf_feature_net(feat93, training):          # stand-in backbone: global mean of the 93 channels
+            seen["feat"], seen["training"] = feat93, training
+            return FakeTFTensor(feat93._t.mean(dim=(1, 2)))
+
+        def ae_invcrf_decode_net(feature):              # stand-in Dense(11) + the (patched) PCA method
+            w11 = FakeTFTensor(feature._t @ torch.from_numpy(proj).cuda())
+            seen["w"] = w11
+            return lin.AEInvcrfDecodeNet().invcrf_pca_w_2_invcrf(w11)
+
+        net = lin.model()
+        net.crf_feature_net, net.ae_invcrf_decode_net = crf_feature_net, ae_invcrf_decode_net
+        SUMMARIES.clear()
+        out = net.call(t_img, training=False)
+        assert seen["training"] is False and seen["feat"].shape == (2, 24, 40, 93)
+        assert np.array_equal(seen["feat"].numpy(), oracle.frontend(img))
+        assert SUMMARIES == [("edge0", (2, 24, 40, 3)), ("edge1", (2, 24, 40, 3))]
+        w_ref = oracle.frontend(img).mean(axis=(1, 2)) @ proj
+        assert np.abs(seen["w"].numpy() - w_ref).max() <= 1e-5
+        ref_out = oracle.increase(oracle.invcrf_pca_w_2_invcrf(seen["w"].numpy(), g0, hinv))
+        assert out.shape == (2, 1024) and np.abs(out.numpy() - ref_out).max() <= 5e-6
 
         monkeypatch.setenv("SHDR_NATIVE", "0")          # A/B switch leaves the stock ops alone
         assert tf_adapter.patch(lin, tfu) is False
