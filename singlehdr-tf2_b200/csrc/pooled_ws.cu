@@ -387,6 +387,10 @@ k_hist_pooled_ws(const float* __restrict__ img, const __grid_constant__ CUtensor
       const bool interior = (y0 >= PB) && (y0 + PT_H + PA <= h) && (x0 >= PB) && (x0 + PT_W + PA <= w);
       float* sRc = sRc0 + (k & 1) * RC_FLOATS;
       if (!interior) {                      // tile-uniform: all consumers take the same branch
+        // sRc is double-buffered by tile parity, but with only two units per tile (C = 12) the ring lets a fast
+        // warp run two tiles ahead of the slowest one, which may still be reading this buffer for tile k - 2:
+        // wait for every consumer to have left it before overwriting
+        named_bar_sync(2, NCONS);
         if (ctid < PT_W) {
           const int gx = min(x0 + ctid, w - 1);
           sRc[ctid] = __fdiv_rn(1.0f, (float)(min(gx + PA, w - 1) - max(gx - PB, 0) + 1));

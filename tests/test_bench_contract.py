@@ -46,3 +46,15 @@ def test_workloads_match_baseline_configs():
     # algorithmic bytes per pixel: 12 in + 4 bytes per output channel
     assert bench.WORKLOADS["config2"][3] == 12 + 4 * 84 and bench.WORKLOADS["config4"][3] == 12 + 4 * 93
     assert bench.WORKLOADS["config3"][3] == 24 and bench.WORKLOADS["config5"][3] == 12 + 4 * 93 + 24
+
+
+def test_both_arms_print_the_same_config():
+    """the driver compares the two arms' `config` dicts (same_config): both come from bench.config_dict"""
+    sys.path.insert(0, ROOT)
+    import bench
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": config_dict(wl,') == 2
+    c = bench.config_dict("config2", 1)
+    assert c["name"] == "config2" and c["batch_per_gpu"] == 32 and c["h"] == 512 and c["w"] == 512
+    assert "no flush needed" in c["l2"] and "flushed" in bench.config_dict("config1", 1)["l2"]
+    assert bench.WORKLOADS["config1"][:3] == (1, 256, 256)

@@ -109,6 +109,17 @@ def test_hist_multi_pooled(shdr_gpu, shape):
     assert_rel(got, t, RTOL_POOL)
 
 
+@pytest.mark.parametrize("shape", [(8, 48, 512, 3), (3, 80, 1024, 3)])
+def test_histogram_layer_pooled_b4_border_interior_mix(shdr_gpu, shape):
+    """B = 4 alone is the two-unit case of the tiled kernel (pooled_ws.cu): many tiles per CTA, border and interior
+    tiles alternating, so that the double-buffered border-scale table is reused while slow warps may still read it."""
+    img = rnd(shape, 99)
+    for _ in range(3):
+        got = shdr_gpu.histogram_layer(shdr_gpu.DeviceArray.from_numpy(img), 4, pool=True).numpy()
+        ref = oracle.avg_pool_same(oracle.histogram_layer(img, 4), 16)
+        assert_rel(got, ref, RTOL_POOL)
+
+
 @pytest.mark.parametrize("B", [4, 5, 16, 21])
 def test_histogram_layer_pooled(shdr_gpu, B):
     img = rnd((1, 37, 70, 3), B)
