@@ -1,11 +1,17 @@
 """CPU oracle for the Linearization-Net per-pixel path -- TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (ShinYwings/SingleHDR-tf2) delegates every
-arithmetic step of this path to TensorFlow >= 2.4 (un-vendored, unpinned,
-``README.md:100``), TensorFlow cannot be installed in the build image, and the
-reference ships no tests, golden vectors or fixtures.  The oracle therefore
-restates the reference's Python op-for-op (same fp32 rounding points, same op
-order) from the call sites cited in every function, and is anchored on
+PARITY UNPINNED w.r.t. TensorFlow's primitives: the reference
+(ShinYwings/SingleHDR-tf2) delegates every arithmetic step of this path to
+TensorFlow >= 2.4 (un-vendored, unpinned, ``README.md:100``), TensorFlow cannot
+be installed in the build image, and the reference ships no tests, golden
+vectors or fixtures.  The oracle restates the reference's Python op-for-op (same
+fp32 rounding points, same op order) from the call sites cited in every
+function.  It IS pinned, bit for bit, against the unmodified reference source
+files executed on a NumPy stand-in for TensorFlow (``tf_reference.py``,
+``standin/tensorflow``, ``tests/golden/ref_standin.npz``,
+``tests/test_reference_golden.py``), which fixes op order, constants, indexing
+and channel order; ``tools/make_tf_golden.py --backend tf`` adds the real-TF
+vectors the day a TensorFlow install exists.  Further anchors:
 
 * the known-answer material the reference does hold (``figure/lin2.png`` B=5
   soft-histogram example; structural facts of ``invemor.txt``), and
