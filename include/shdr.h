@@ -85,6 +85,12 @@ int shdr_hist_multi_f32(const float* img, float* out, int n, int h, int w,
 int shdr_frontend_f32(const float* img, float* out, int n, int h, int w,
                       int pool_k, void* stream);
 
+/* shdr_frontend_f32(pool_k = 0) with the 93-channel tensor rounded to bfloat16 (round to nearest even) on the way
+ * out: out_bf16 is [n,h,w,93] of 16-bit values (186 B/px instead of 372).  The reduced-precision output flag of
+ * SURVEY.md 8(f) rank 2 for a consumer (crfFeatureNet.conv1, linearization_net.py:91,107) that runs in bf16; it
+ * changes numerics and is therefore never what the parity-gated default path or bench.py's headline uses. */
+int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h, int w, void* stream);
+
 /* ---- (B) inverse-CRF stage ----------------------------------------------- */
 
 /* AEInvcrfDecodeNet.invcrf_pca_w_2_invcrf (:231-253): curve[b,1024] = g0 + hinv.w[b,11];
@@ -117,6 +123,17 @@ int shdr_apply_rf_ex_f32(const float* x, const float* rf, float* y, float* clipp
 int shdr_linearize_ex_f32(const float* x, const float* w, float* y, float* curve_out,
                           float* clipped_out, float* alpha_out, int b,
                           long long pixels_per_item, int clip, float thr, void* stream);
+
+/* Synthetic-LDR generator: the per-pixel part of _preprocessing (train.py:28-51, joint_training.py:26-47), one pass:
+ *   x = relu(hdr*t[b] + noise_s * (sigma_s[b,c] * hdr*t[b]) + sigma_c[b,c] * noise_c);   c = clip(x, 0, 1);
+ *   l = apply_rf(c, crf[b]);   q = round(l * 255)  (half to even, as float)
+ * hdr / noise_s / noise_c are [b, pixels_per_item, 3]; the unit-normal noise samples are inputs (the random generator
+ * stays with the caller); t is [b], sigma_s / sigma_c are [b,3], crf is [b,k] (forward CRFs; the reference draws them
+ * from dorfCurves.txt, which its repository does not ship).  Each output ([b,pixels,3]) may be NULL. */
+int shdr_synth_ldr_f32(const float* hdr, const float* t, const float* sigma_s, const float* sigma_c,
+                       const float* noise_s, const float* noise_c, const float* crf,
+                       float* out_hdr_t, float* out_clipped, float* out_ldr, float* out_quant,
+                       int b, long long pixels_per_item, int k, void* stream);
 
 /* ---- (C) reverse-mode gradients (training steps: train.py:186-194,
  *          joint_training.py:156-186, finetune_real_dataset.py:149-178) -------------
@@ -156,6 +173,9 @@ int shdr_dl_frontend(const struct DLManagedTensor* img, int pool_k, void* stream
                      struct DLManagedTensor** out);
 int shdr_dl_sobel6(const struct DLManagedTensor* img, void* stream,
                    struct DLManagedTensor** out);
+/* shdr_frontend_bf16 on DLPack tensors: the result is a kDLBfloat / 16-bit tensor [n,h,w,93] */
+int shdr_dl_frontend_bf16(const struct DLManagedTensor* img, void* stream,
+                          struct DLManagedTensor** out);
 int shdr_dl_soft_hist(const struct DLManagedTensor* img, int bins, int pool_k,
                       void* stream, struct DLManagedTensor** out);
 int shdr_dl_invcrf_build(const struct DLManagedTensor* w, int monotone, void* stream,

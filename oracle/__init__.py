@@ -35,6 +35,6 @@ from .np_oracle import (  # noqa: F401
     sobel_edges6, histogram_layer, avg_pool_same, frontend, hist_multi,
     parse_invemor, parse_table, invcrf_pca_w_2_invcrf, increase, apply_rf,
     linearize, hist_centers,
-    clip01, alpha_mask, linearize_ex,
+    clip01, alpha_mask, linearize_ex, synth_ldr,
     apply_rf_grad, increase_grad, invcrf_pca_grad, histogram_layer_grad, sobel_edges6_grad, frontend_grad,
 )

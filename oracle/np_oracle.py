@@ -246,6 +246,27 @@ def linearize_ex(x, rf, thr, clip=True, dtype=np.float32):
     return c, y, alpha_mask(y, thr, dtype)
 
 
+def synth_ldr(hdr, t, sigma_s, sigma_c, noise_s, noise_c, crf, dtype=np.float32):
+    """The per-pixel part of ``_preprocessing`` (train.py:28-51): returns (_hdr_t, clipped_hdr_t, ldr, quantized_hdr).
+    ``noise_s`` / ``noise_c`` stand for the two ``tf.random.normal`` tensors, ``sigma_s`` / ``sigma_c`` ([b,3]) for the
+    ``0.08/6 * uniform`` and ``0.005 * uniform`` factors of shape [b,1,1,3]."""
+    hdr = np.asarray(hdr, dtype=dtype)
+    b = hdr.shape[0]
+    _hdr_t = hdr * np.asarray(t, dtype=dtype).reshape(b, 1, 1, 1)                      # :31
+    ss = np.asarray(sigma_s, dtype=dtype).reshape(b, 1, 1, 3)
+    sc = np.asarray(sigma_c, dtype=dtype).reshape(b, 1, 1, 3)
+    noise_s_map = ss * _hdr_t                                                        # :37
+    noise_s_t = np.asarray(noise_s, dtype=dtype) * noise_s_map                       # :38
+    temp_x = _hdr_t + noise_s_t                                                      # :39
+    noise_c_t = sc * np.asarray(noise_c, dtype=dtype)                                # :40
+    temp_x = temp_x + noise_c_t                                                      # :41
+    _hdr_t = np.maximum(temp_x, dtype(0.0))                                          # :42 relu
+    clipped = clip01(_hdr_t, dtype)                                                  # :45
+    ldr = apply_rf(clipped, crf, dtype)                                              # :48
+    quant = np.round(ldr * dtype(255.0))                                             # :51 tf.round: half to even
+    return _hdr_t, clipped, ldr, quant.astype(dtype)
+
+
 # --------------------------------------------------------------------------
 # (D) reverse-mode gradients: what TensorFlow's autodiff computes for the reference's op sequences
 #     (train.py:186-194, joint_training.py:156-186, finetune_real_dataset.py:149-178).  [TF-sem]: floor / cast /

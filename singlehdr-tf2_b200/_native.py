@@ -47,12 +47,14 @@ SIGNATURES = {
     "shdr_soft_hist_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "shdr_hist_multi_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "shdr_frontend_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "shdr_frontend_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "shdr_invcrf_build_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "shdr_increase_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "shdr_apply_rf_f32": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),
     "shdr_linearize_f32": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _vp]),
     "shdr_apply_rf_ex_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _i, C.c_float, _vp]),
     "shdr_linearize_ex_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, C.c_float, _vp]),
+    "shdr_synth_ldr_f32": (_i, [_vp] * 11 + [_i, _ll, _i, _vp]),
     "shdr_apply_rf_bwd_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     "shdr_increase_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "shdr_invcrf_build_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
@@ -60,6 +62,7 @@ SIGNATURES = {
     "shdr_soft_hist_bwd_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "shdr_dl_frontend": (_i, [_dl, _i, _vp, _dlp]),
     "shdr_dl_sobel6": (_i, [_dl, _vp, _dlp]),
+    "shdr_dl_frontend_bf16": (_i, [_dl, _vp, _dlp]),
     "shdr_dl_soft_hist": (_i, [_dl, _i, _i, _vp, _dlp]),
     "shdr_dl_invcrf_build": (_i, [_dl, _i, _vp, _dlp]),
     "shdr_dl_increase": (_i, [_dl, _vp, _dlp]),

@@ -13,6 +13,8 @@
 // channels at an odd word stride -> bank-conflict free) and then streams the 47.6 KB strip to HBM
 // as flat, fully coalesced 128-bit stores.  Strips are taken over the flattened pixel index of the
 // whole batch, so strip bases are 16-B aligned for any image width.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace shdr {
@@ -36,7 +38,10 @@ __device__ __forceinline__ void hist_bins_pow2(float v, float* o /* stride 3 bet
   }
 }
 
-template <bool FULL, int HMASK>
+// BF16: the strip is rounded to bfloat16 (round to nearest even) while it is streamed out -- the reduced-precision
+// output flag of SURVEY.md 8(f) rank 2 (halves the 372 B/px write that dominates this kernel's roofline time; changes
+// numerics, so it is a separate entry point and never the parity-gated default).
+template <bool FULL, int HMASK, bool BF16 = false>
 __global__ void __launch_bounds__(STRIP)
 k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx, int h, int w, int vec_ok) {
   using L = StripLayout<FULL, HMASK>;
@@ -99,6 +104,23 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
   // stream the strip out: flat over [pixels in strip] x CH
   const int npx_strip = min(STRIP, npx - p0);
   const int nfl = npx_strip * CH;
+  if (BF16) {
+    // CHP == CH here (93 is odd); the strip base p0 * CH * 2 bytes is 16-byte aligned (p0 is a multiple of 128)
+    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)p0 * CH;
+    const int nv = vec_ok ? (nfl >> 3) : 0;               // 8 values = 128 bits
+    uint4* o4 = reinterpret_cast<uint4*>(ob);
+    for (int i = tid; i < nv; i += STRIP) {
+      const float* q = s + 8 * i;
+      __nv_bfloat162 a = __floats2bfloat162_rn(q[0], q[1]), b = __floats2bfloat162_rn(q[2], q[3]);
+      __nv_bfloat162 c = __floats2bfloat162_rn(q[4], q[5]), d = __floats2bfloat162_rn(q[6], q[7]);
+      uint4 v;
+      v.x = *reinterpret_cast<unsigned*>(&a); v.y = *reinterpret_cast<unsigned*>(&b);
+      v.z = *reinterpret_cast<unsigned*>(&c); v.w = *reinterpret_cast<unsigned*>(&d);
+      __stcs(o4 + i, v);
+    }
+    for (int i = (nv << 3) + tid; i < nfl; i += STRIP) ob[i] = __float2bfloat16_rn(s[i]);
+    return;
+  }
   float* og = out + (size_t)p0 * CH;
   if (CHP == CH) {
     int done = 0;
@@ -121,10 +143,10 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
   }
 }
 
-template <bool FULL, int HMASK>
+template <bool FULL, int HMASK, bool BF16 = false>
 static int launch_strip(const float* img, float* out, long long npx, int h, int w, cudaStream_t st) {
   const unsigned grid = (unsigned)((npx + STRIP - 1) / STRIP);
-  k_frontend_strip<FULL, HMASK><<<grid, STRIP, 0, st>>>(img, out, (int)npx, h, w, aligned16(out) ? 1 : 0);
+  k_frontend_strip<FULL, HMASK, BF16><<<grid, STRIP, 0, st>>>(img, out, (int)npx, h, w, aligned16(out) ? 1 : 0);
   SHDR_LAUNCH_CHECK("k_frontend_strip");
   return SHDR_OK;
 }
@@ -322,4 +344,13 @@ extern "C" int shdr_frontend_f32(const float* img, float* out, int n, int h, int
   rc = launch_sobel_generic(img, out, npx, h, w, 3, SHDR_FRONTEND_CH, 3, st, g.dev);
   if (rc != SHDR_OK) return rc;
   return launch_hist_pooled(img, out, n, h, w, bins, 3, SHDR_FRONTEND_CH, 9, st);
+}
+
+extern "C" int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h, int w, void* stream) {
+  int rc = check_image("frontend_bf16", img, (const float*)out_bf16, n, h, w, 3);
+  if (rc != SHDR_OK) return rc < 0 ? rc : SHDR_OK;
+  SHDR_REQUIRE(h >= 2 && w >= 2, "frontend_bf16: REFLECT padding needs h >= 2 and w >= 2 (got %d x %d)", h, w);
+  DeviceGuard g(out_bf16);
+  if (g.status != SHDR_OK) return g.status;
+  return launch_strip<true, 7, true>(img, (float*)out_bf16, (long long)n * h * w, h, w, (cudaStream_t)stream);
 }

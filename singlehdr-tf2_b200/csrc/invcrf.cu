@@ -402,6 +402,55 @@ static int launch_apply(const float* x, const float* rf, float* y, int b, long l
              : launch_apply_t<false, false>(x, rf, y, b, n, k, st, dev, pdl);
 }
 
+
+// ---- synthetic-LDR generator, the per-pixel part of _preprocessing (train.py:28-50, joint_training.py:26-46), fused:
+//   x  = hdr * t[b]                                   exposure                          (:31)
+//   x  = relu(x + n_s * (sigma_s[b,c] * x) + sigma_c[b,c] * n_c)   Poisson + Gaussian noise (:34-42)
+//   c  = clip_by_value(x, 0, 1)                       dynamic-range clipping            (:45)
+//   l  = apply_rf(c, crf[b])                          camera response                   (:48)
+//   q  = round(l * 255)                               quantisation (tf.round: half to even) (:51)
+// The unit-normal samples n_s, n_c are INPUTS (TensorFlow's random generator stays in TensorFlow); sigma_s / sigma_c
+// are the reference's per-image, per-channel factors [b,3].  Outputs (each nullable): x (_hdr_t), c, l, q as float.
+template <bool SMEM>
+__global__ void __launch_bounds__(APPLY_THREADS)
+k_synth_ldr(const float* __restrict__ hdr, const float* __restrict__ t, const float* __restrict__ sig_s,
+            const float* __restrict__ sig_c, const float* __restrict__ n_s, const float* __restrict__ n_c,
+            const float* __restrict__ rf, float* __restrict__ o_x, float* __restrict__ o_c, float* __restrict__ o_l,
+            float* __restrict__ o_q, long long px_per_item, int k, int chunks_per_item, long long px_per_chunk) {
+  extern __shared__ float2 tab[];
+  const int tid = threadIdx.x;
+  const long long item = blockIdx.x / chunks_per_item;
+  const int chunk = blockIdx.x - (int)(item * chunks_per_item);
+  const float* r = rf + item * k;
+  if (SMEM) {
+    for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
+    __syncthreads();
+  }
+  const float km1 = (float)(k - 1);
+  const int kmax = k - 1;
+  const float ti = t[item];
+  float ss[3], sc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { ss[c] = sig_s[item * 3 + c]; sc[c] = sig_c[item * 3 + c]; }
+  const long long p0 = (long long)chunk * px_per_chunk;
+  const long long p1 = min(p0 + px_per_chunk, px_per_item);
+  const long long base = item * px_per_item * 3;
+  for (long long e = p0 * 3 + tid; e < p1 * 3; e += APPLY_THREADS) {
+    const int c = (int)(e % 3);
+    const float x0 = __fmul_rn(__ldg(hdr + base + e), ti);                              // hdr * t
+    const float ns = __fmul_rn(__ldg(n_s + base + e), __fmul_rn(ss[c], x0));            // normal * (sigma_s * _hdr_t)
+    float x = __fadd_rn(x0, ns);
+    x = __fadd_rn(x, __fmul_rn(sc[c], __ldg(n_c + base + e)));                          // + sigma_c * normal
+    x = fmaxf(x, 0.0f);                                                                 // relu
+    const float cl = clip01(x);
+    const float l = lerp_lookup<SMEM>(cl, tab, r, km1, kmax);
+    if (o_x) o_x[base + e] = x;
+    if (o_c) o_c[base + e] = cl;
+    if (o_l) o_l[base + e] = l;
+    if (o_q) o_q[base + e] = rintf(__fmul_rn(l, 255.0f));                               // round half to even
+  }
+}
+
 }  // namespace shdr
 
 using namespace shdr;
@@ -472,4 +521,41 @@ extern "C" int shdr_linearize_ex_f32(const float* x, const float* w, float* y, f
   if (rc != SHDR_OK || pixels_per_item == 0) return rc;
   return launch_apply_px(x, curve_out, y, clipped_out, alpha_out, b, pixels_per_item, SHDR_EMOR_SAMPLES, clip, thr,
                          (cudaStream_t)stream, g.dev, true);
+}
+
+extern "C" int shdr_synth_ldr_f32(const float* hdr, const float* t, const float* sigma_s, const float* sigma_c,
+                                  const float* noise_s, const float* noise_c, const float* crf, float* out_hdr_t,
+                                  float* out_clipped, float* out_ldr, float* out_quant, int b,
+                                  long long pixels_per_item, int k, void* stream) {
+  SHDR_REQUIRE(b >= 0 && pixels_per_item >= 0, "synth_ldr: b=%d pixels_per_item=%lld", b, pixels_per_item);
+  SHDR_REQUIRE(k >= 1, "synth_ldr: k=%d", k);
+  SHDR_REQUIRE(out_hdr_t || out_clipped || out_ldr || out_quant, "synth_ldr: every output is NULL");
+  if (b == 0 || pixels_per_item == 0) return SHDR_OK;
+  SHDR_REQUIRE(hdr && t && sigma_s && sigma_c && noise_s && noise_c && crf, "synth_ldr: NULL input");
+  float* any = out_ldr ? out_ldr : (out_quant ? out_quant : (out_clipped ? out_clipped : out_hdr_t));
+  DeviceGuard g(any);
+  if (g.status != SHDR_OK) return g.status;
+  const long long quantum = 4LL * APPLY_THREADS;
+  long long per_chunk = quantum * 8;
+  const long long want = (long long)sm_count(g.dev) * 8;
+  while (per_chunk > quantum && (long long)b * ((pixels_per_item + per_chunk - 1) / per_chunk) < want) per_chunk >>= 1;
+  const long long chunks = (pixels_per_item + per_chunk - 1) / per_chunk;
+  const long long grid = (long long)b * chunks;
+  SHDR_REQUIRE(grid > 0 && grid <= 0x7fffffffLL, "synth_ldr: grid of %lld CTAs is out of range", grid);
+  const bool smem = (size_t)k * sizeof(float2) <= 200 * 1024;
+  const size_t bytes = smem ? (size_t)k * sizeof(float2) : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (smem) {
+    if (bytes > 48 * 1024)
+      SHDR_CUDA(cudaFuncSetAttribute(k_synth_ldr<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k_synth_ldr<true><<<(unsigned)grid, APPLY_THREADS, bytes, st>>>(hdr, t, sigma_s, sigma_c, noise_s, noise_c, crf,
+                                                                   out_hdr_t, out_clipped, out_ldr, out_quant,
+                                                                   pixels_per_item, k, (int)chunks, per_chunk);
+  } else {
+    k_synth_ldr<false><<<(unsigned)grid, APPLY_THREADS, 0, st>>>(hdr, t, sigma_s, sigma_c, noise_s, noise_c, crf,
+                                                                out_hdr_t, out_clipped, out_ldr, out_quant,
+                                                                pixels_per_item, k, (int)chunks, per_chunk);
+  }
+  SHDR_LAUNCH_CHECK("k_synth_ldr");
+  return SHDR_OK;
 }

@@ -56,12 +56,19 @@ def _describe(managed_ptr):
     return (t.data or 0) + t.byte_offset, shape, int(t.device.device_id), int(t.device.device_type)
 
 
+def _itemsize(managed_ptr):
+    t = C.cast(managed_ptr, C.POINTER(_DLManagedTensor)).contents.dl_tensor
+    return int(t.dtype.bits) // 8
+
+
 class DeviceArray:
-    """A float32 CUDA tensor owned by libshdr (compact row-major)."""
+    """A CUDA tensor owned by libshdr (compact row-major): float32, or bfloat16 for the reduced-precision front end
+    (``numpy()`` then returns the 16-bit patterns as ``uint16``)."""
 
     def __init__(self, managed_ptr):
         self._m = managed_ptr
         self.ptr, self.shape, self.device, _ = _describe(managed_ptr)
+        self.itemsize = _itemsize(managed_ptr)
 
     # -- construction
     @classmethod
@@ -89,7 +96,7 @@ class DeviceArray:
 
     @property
     def nbytes(self):
-        return self.size * 4
+        return self.size * self.itemsize
 
     def _alive(self):
         if self._m is None:
@@ -97,7 +104,7 @@ class DeviceArray:
 
     def numpy(self, stream=None):
         self._alive()
-        out = np.empty(self.shape, np.float32)
+        out = np.empty(self.shape, np.float32 if self.itemsize == 4 else np.uint16)
         if out.size:
             # the copy stream waits for the producing kernel (whatever stream it ran on)
             N.check(N.lib.shdr_dl_wait_ready(self._m, getattr(stream, "handle", stream), 0))

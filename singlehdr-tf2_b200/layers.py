@@ -86,6 +86,13 @@ def frontend(img, pool=False, stream=None):
     return _run_dl(N.lib.shdr_dl_frontend, [img], POOL_K if pool else 0, stream=stream)
 
 
+def frontend_bf16(img, stream=None):
+    """:func:`frontend` (un-pooled) with the 93-channel tensor rounded to bfloat16 on the way out -- the
+    reduced-precision output flag for a consumer that runs ``crfFeatureNet.conv1`` in bf16 (half the bytes written and
+    handed over).  Changes numerics (8 mantissa bits): never the default, never what the parity tests gate."""
+    return _run_dl(N.lib.shdr_dl_frontend_bf16, [img], stream=stream)
+
+
 def hist_multi(img, pool=False, stream=None):
     """``concat([hist4, hist8, hist16], -1)`` -> ``[b,h,w,84]`` in one launch."""
     (b,) = _dev_inputs(stream, img)
@@ -218,6 +225,33 @@ def linearize_ex(x, invcrf_pca_w=None, rf=None, clip=True, alpha_threshold=None,
         out["clipped"] = cl
     if al is not None:
         out["alpha"] = al
+    for v in out.values():
+        v.mark_ready(stream)
+    return out
+
+
+def synth_ldr(hdr, t, sigma_s, sigma_c, noise_s, noise_c, crf, outputs=("hdr_t", "clipped", "ldr", "quant"), stream=None):
+    """The per-pixel part of the reference's synthetic-LDR generator ``_preprocessing`` (train.py:28-51,
+    joint_training.py:26-47) in one pass: exposure ``hdr*t``, Poisson + Gaussian noise, relu, clip to [0,1], forward
+    CRF (``apply_rf``), 8-bit quantisation.  ``hdr``/``noise_s``/``noise_c``: ``[b,h,w,3]`` (unit-normal samples are
+    inputs: the random generator stays with the caller); ``t [b]``; ``sigma_s``/``sigma_c [b,3]``; ``crf [b,k]``.
+    Returns a dict with the requested outputs (``hdr_t``, ``clipped``, ``ldr``, ``quant`` = ``round(ldr*255)``)."""
+    bh, bt, bss, bsc, bns, bnc, bcrf = _dev_inputs(stream, hdr, t, sigma_s, sigma_c, noise_s, noise_c, crf)
+    b = bh.shape[0] if bh.shape else 0
+    if (len(bh.shape) < 2 or bh.shape[-1] != 3 or tuple(bns.shape) != tuple(bh.shape) or tuple(bnc.shape) != tuple(bh.shape)
+            or int(np.prod(bt.shape)) != b or tuple(bss.shape) != (b, 3) or tuple(bsc.shape) != (b, 3)
+            or len(bcrf.shape) != 2 or bcrf.shape[0] != b):
+        raise ValueError(f"synth_ldr: shape mismatch: hdr {bh.shape}, t {bt.shape}, sigma {bss.shape}/{bsc.shape}, "
+                         f"noise {bns.shape}/{bnc.shape}, crf {bcrf.shape}")
+    names = ("hdr_t", "clipped", "ldr", "quant")
+    bad = [o for o in outputs if o not in names]
+    if bad or not outputs:
+        raise ValueError(f"synth_ldr: outputs must be a non-empty subset of {names}, got {outputs}")
+    out = {o: DeviceArray.empty(bh.shape, bh.device) for o in outputs}
+    ptr = [out[nm].ptr if nm in out else None for nm in names]
+    npx = int(np.prod(bh.shape[1:-1], dtype=np.int64))
+    N.check(N.lib.shdr_synth_ldr_f32(bh.ptr, bt.ptr, bss.ptr, bsc.ptr, bns.ptr, bnc.ptr, bcrf.ptr, *ptr, b, npx,
+                                     bcrf.shape[1], _stream(stream)))
     for v in out.values():
         v.mark_ready(stream)
     return out

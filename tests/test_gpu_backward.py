@@ -142,3 +142,27 @@ def test_linearize_ex_from_weights(shdr_gpu, emor):
     assert np.array_equal(out["alpha"].numpy(), a)
     y2, _ = shdr_gpu.linearize(D(c), D(w))
     assert np.array_equal(y2.numpy(), y)
+
+
+# ---------------------------------------------------------------- synthetic-LDR generator
+@pytest.mark.parametrize("shape,k", [((3, 20, 28, 3), 1024), ((1, 7, 5, 3), 1024), ((2, 16, 16, 3), 256)])
+def test_synth_ldr(shdr_gpu, shape, k):
+    rng = np.random.default_rng(sum(shape) + k)
+    b = shape[0]
+    hdr = (rng.random(shape) ** 3 * 4.0).astype(np.float32)                  # HDR radiance, some above 1 after exposure
+    t = (2.0 ** rng.uniform(-3, 3, b)).astype(np.float32)
+    ss = (0.08 / 6 * rng.random((b, 3))).astype(np.float32)
+    sc = (0.005 * rng.random((b, 3))).astype(np.float32)
+    ns = rng.normal(size=shape).astype(np.float32)
+    nc = rng.normal(size=shape).astype(np.float32)
+    crf = (np.linspace(0, 1, k, dtype=np.float32)[None] ** rng.uniform(0.3, 0.8, (b, 1))).astype(np.float32)
+    D = shdr_gpu.DeviceArray.from_numpy
+    out = shdr_gpu.synth_ldr(D(hdr), D(t), D(ss), D(sc), D(ns), D(nc), D(crf))
+    x, c, l, q = oracle.synth_ldr(hdr, t, ss, sc, ns, nc, crf)
+    assert np.array_equal(out["hdr_t"].numpy(), x)          # same op order and roundings: bit-exact
+    assert np.array_equal(out["clipped"].numpy(), c)
+    assert np.array_equal(out["ldr"].numpy(), l)
+    assert np.array_equal(out["quant"].numpy(), q)
+    assert q.min() >= 0 and q.max() <= 255
+    only = shdr_gpu.synth_ldr(D(hdr), D(t), D(ss), D(sc), D(ns), D(nc), D(crf), outputs=("ldr",))
+    assert set(only) == {"ldr"} and np.array_equal(only["ldr"].numpy(), l)

@@ -420,3 +420,18 @@ def test_no_writes_outside_the_output(shdr_gpu, shape):
     assert_rel(fp.reshape(n, h, w, 93)[..., 9:], oracle.hist_multi(img, pool_k=16), RTOL_POOL)
     curve = shdr_gpu.DeviceArray.empty((n, 1024))
     run(px * 3, lambda p: N.check(N.lib.shdr_linearize_f32(d_img.ptr, d_w.ptr, p, curve.ptr, n, h * w * 3, None)))
+
+
+def _to_bf16_bits(a):
+    """float32 -> bfloat16 bit patterns, round to nearest even (what __float2bfloat16_rn does for finite values)"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+@pytest.mark.parametrize("shape", [(2, 24, 40, 3), (1, 5, 1027, 3), (3, 17, 31, 3)])
+def test_frontend_bf16_is_the_rounded_fp32_front_end(shdr_gpu, shape):
+    """SURVEY 8(f) rank 2 (reduced-precision output flag): exactly the fp32 front end rounded to bfloat16"""
+    img = rnd(shape, sum(shape) + 5)
+    got = shdr_gpu.frontend_bf16(shdr_gpu.DeviceArray.from_numpy(img))
+    assert got.itemsize == 2 and got.shape == shape[:3] + (93,)
+    assert np.array_equal(got.numpy(), _to_bf16_bits(oracle.frontend(img)))
