@@ -248,16 +248,16 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
   }
 }
 
-// Sobel of one (pixel, colour) at image row y, column gx: same tap order as k_frontend_strip (frontend.cu)
-__device__ __forceinline__ void sobel_at(const float* __restrict__ q, int y, int gx, int h, int w, float& v, float& dy,
-                                         float& dx) {
-  const long long oym = (long long)(reflect1(y - 1, h) - y) * w * 3;
-  const long long oyp = (long long)(reflect1(y + 1, h) - y) * w * 3;
-  const int oxm = (reflect1(gx - 1, w) - gx) * 3;
-  const int oxp = (reflect1(gx + 1, w) - gx) * 3;
-  const float p00 = __ldg(q + oym + oxm), p01 = __ldg(q + oym), p02 = __ldg(q + oym + oxp);
+// Sobel of one (pixel, colour): q points at the pixel's colour sample in row y; up / dn are the offsets (in floats)
+// of the rows above / below and oxm / oxp those of the columns left / right, REFLECT already applied (-1 -> 1,
+// n -> n-2).  Same tap order as k_frontend_strip (frontend.cu).
+__device__ __forceinline__ void sobel_at(const float* __restrict__ q, int up, int dn, int oxm, int oxp, float& v,
+                                         float& dy, float& dx) {
+  const float* qu = q + up;
+  const float* qd = q + dn;
+  const float p00 = __ldg(qu + oxm), p01 = __ldg(qu), p02 = __ldg(qu + oxp);
   const float p10 = __ldg(q + oxm), p12 = __ldg(q + oxp);
-  const float p20 = __ldg(q + oyp + oxm), p21 = __ldg(q + oyp), p22 = __ldg(q + oyp + oxp);
+  const float p20 = __ldg(qd + oxm), p21 = __ldg(qd), p22 = __ldg(qd + oxp);
   v = __ldg(q);
   dy = -p00;
   dy = __fadd_rn(dy, -2.0f * p01);
@@ -342,6 +342,22 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
       const int gx = k.x0 + gtid;
       nx = min(max(min(gx + HR, p.w - 1) - max(gx - HL, 0) + 1, 0), PK);
     }
+    // FULL: this lane's (pixel, colour) item of every row of the task (64 pixels x 3 colours over the group's 192 lanes)
+    int fpx = -1, fc = 0, oxm = 0, oxp = 0;
+    const float* fq = nullptr;             // the item's sample in row 0 of the image
+    const int rs3 = p.w * 3;
+    if (FULL) {
+      const int item = sub * 32 + lane;
+      const int px = item / 3;
+      fc = item - px * 3;
+      const int gx = k.x0 + px;
+      if (gx < p.w) {
+        fpx = px;
+        oxm = (reflect1(gx - 1, p.w) - gx) * 3;
+        oxp = (reflect1(gx + 1, p.w) - gx) * 3;
+        fq = p.img + ((long long)k.n * p.h * p.w + gx) * 3 + fc;
+      }
+    }
     // this group's rows of the task: those whose emission index q0 + (y - y0) has parity g
     const unsigned q0 = q;
     const int nrows = k.y1 - k.y0;
@@ -354,16 +370,8 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
       const unsigned qq = q0 + (unsigned)yy;
       float* stg = stg0 + par * (SW * CO);
       float fv = 0.f, fdy = 0.f, fdx = 0.f;
-      int fpx = -1, fc = 0;
-      if (FULL) {                          // img + Sobel of one (pixel, colour) of this row, loads issued early
-        const int item = sub * 32 + lane;  // 0..191 = 64 pixels x 3 colours
-        const int px = item / 3;
-        fc = item - px * 3;
-        if (k.x0 + px < p.w) {
-          fpx = px;
-          sobel_at(p.img + (((long long)k.n * p.h + y) * p.w + k.x0 + px) * 3 + fc, y, k.x0 + px, p.h, p.w, fv, fdy, fdx);
-        }
-      }
+      if (FULL && fpx >= 0)                // img + Sobel of this lane's (pixel, colour); the loads are issued early
+        sobel_at(fq + (long long)y * rs3, y == 0 ? rs3 : -rs3, y == p.h - 1 ? -rs3 : rs3, oxm, oxp, fv, fdy, fdx);
       const int ny = min(y + HR, p.h - 1) - max(y - HL, 0) + 1;
       const unsigned s = qq % NST, ph = (qq / NST) & 1u;
       mbar_wait(bars + s, ph);             // producers filled this stage
