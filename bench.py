@@ -485,6 +485,22 @@ def run_native(args):
         if isinstance(subs["config1"], dict) and "ms_per_step" in subs["config1"]:
             subs["config1"]["latency_us"] = subs["config1"]["ms_per_step"] * 1e3
 
+    # ---- host-side cost of one op through the DLPack surface the TF adapter uses (borrow the inputs, stream-ordered
+    # allocation of the output, launch, ready event, hand the result back as a capsule); a torch tensor stands in for
+    # the TF tensor
+    dl_us = None
+    if rank == 0:
+        xs = torch.rand((1, 64, 64, 3), device=dev)
+        rf_small = torch.linspace(0, 1, 1024, device=dev).reshape(1, 1024).contiguous()
+        for _ in range(20):
+            torch.utils.dlpack.from_dlpack(shdr.apply_rf(xs, rf_small).__dlpack__())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(200):
+            torch.utils.dlpack.from_dlpack(shdr.apply_rf(xs, rf_small).__dlpack__())
+        torch.cuda.synchronize()
+        dl_us = (time.perf_counter() - t0) / 200 * 1e6
+
     if rank == 0:
         peak, peak_src = load_peak()
         achieved = px * bpp / (kern_ms * 1e-3) / 1e9
@@ -503,6 +519,7 @@ def run_native(args):
                     "note": "ceiling = the same H2D + D2H bytes as plain pinned cudaMemcpyAsync calls, all ranks at once"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "dlpack_call_us": dl_us,
         }
         if subs:
             line["sub_records"] = subs
