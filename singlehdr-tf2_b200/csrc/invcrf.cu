@@ -199,12 +199,12 @@ k_apply_rf(const float* __restrict__ x, const float* __restrict__ rf, float* __r
     // x does not depend on the curve kernel: when this grid runs as a programmatic dependent of k_curve
     // (shdr_linearize_f32) the first batch of loads is in flight while k_curve finishes
     float4 in[APPLY_UNROLL];
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
 #pragma unroll
     for (int u = 0; u < APPLY_UNROLL; ++u) {
       const long long vv = v + u * APPLY_THREADS;
       if (vv < v1) in[u] = ld_stream4(x4 + vv);
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
     if (SMEM) {
       for (int i = tid; i < k; i += APPLY_THREADS) tab[i] = make_float2(r[i], r[min(i + 1, k - 1)]);
       __syncthreads();
