@@ -435,3 +435,31 @@ def test_frontend_bf16_is_the_rounded_fp32_front_end(shdr_gpu, shape):
     got = shdr_gpu.frontend_bf16(shdr_gpu.DeviceArray.from_numpy(img))
     assert got.itemsize == 2 and got.shape == shape[:3] + (93,)
     assert np.array_equal(got.numpy(), _to_bf16_bits(oracle.frontend(img)))
+
+
+@pytest.mark.parametrize("value", [0.0, 1.0, 0.5, 0.125, 0.375, 0.0625, 1.0 / 32.0, 31.0 / 32.0, 0.3])
+def test_pooled_constant_images(shdr_gpu, value):
+    """Constant images: at a bin centre every vote of that bin is exactly 1.0, so every interior 16x16 window sums to
+    256 * 2^24 = 2^32 in the integer pipeline -- the overflow guard of pooled_slide.cu (one capped column per window)
+    must give exactly 1.0 (within fp32 rounding), and the other bins must be exactly 0."""
+    img = np.full((2, 40, 136, 3), value, np.float32)
+    got = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    ref = oracle.hist_multi(img, pool_k=16)
+    assert_rel(got, ref, RTOL_POOL)
+    assert np.array_equal(got == 0, ref == 0)
+    full = shdr_gpu.frontend(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    assert_rel(full[..., 9:], ref, RTOL_POOL)
+    assert np.array_equal(full[..., :3], img) and np.all(full[..., 3:9] == 0)
+
+
+def test_pooled_sparse_votes_stay_relative(shdr_gpu):
+    """One grazing pixel in an otherwise empty bin: the pooled value is ~1e-9, and still within 1e-5 RELATIVE (the
+    integer window sums are exact; an fp32 sliding sum would lose it)."""
+    img = np.full((1, 48, 80, 3), 0.9, np.float32)
+    img[0, 20, 40] = [0.375 - 2.0 ** -20, 0.625 + 2.0 ** -21, 0.125 - 2.0 ** -22]      # votes of 2^-18 .. 2^-20 for B = 4
+    got = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    ref = oracle.hist_multi(img, pool_k=16)
+    t64 = oracle.hist_multi(img, pool_k=16, dtype=np.float64)
+    assert_rel(got, ref, RTOL_POOL)
+    assert_rel(got, t64, RTOL_POOL)
+    assert ((ref > 0) & (ref < 1e-6)).any()               # the case really contains tiny non-zero pooled values
