@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 
 SUMMARIES = []
+PY_FUNCTION_CALLS = []
 
 
 class FakeTFTensor:
@@ -35,13 +36,24 @@ class FakeTFTensor:
     def __getitem__(self, idx):
         return FakeTFTensor(self._t[idx].contiguous())
 
+    def set_shape(self, shape):
+        assert tuple(shape) == self.shape, (tuple(shape), self.shape)      # the adapter's static-shape functions
 
-def _install_fake_tf():
+
+def _install_fake_tf(eager=True):
     import torch
     tf = types.ModuleType("tensorflow")
     tf.float32 = "float32"
-    tf.executing_eagerly = lambda: True
-    tf.py_function = lambda fn, args, dtype: fn(*args)
+    tf.executing_eagerly = lambda: eager
+
+    def py_function(fn, args, dtype):
+        """graph mode: the adapter wraps every native call (forward and gradient) in tf.py_function and restores the
+        static shape with set_shape; here the wrapped function simply runs, and the shapes set are recorded"""
+        PY_FUNCTION_CALLS.append(dtype)
+        out = fn(*args)
+        assert isinstance(dtype, list) == isinstance(out, tuple)
+        return list(out) if isinstance(out, tuple) else out
+    tf.py_function = py_function
     tf.cast = lambda x, dtype: x
     tf.summary = types.SimpleNamespace(image=lambda name, t: SUMMARIES.append((name, t.shape)))
 
@@ -61,10 +73,12 @@ def _install_fake_tf():
     return tf
 
 
-def test_patch_reference_modules(shdr_gpu, emor, tmp_path, monkeypatch):
+@pytest.mark.parametrize("eager", [True, False], ids=["eager", "graph"])
+def test_patch_reference_modules(shdr_gpu, emor, tmp_path, monkeypatch, eager):
     import torch
     from shdr import tf_adapter
-    _install_fake_tf()
+    _install_fake_tf(eager)
+    PY_FUNCTION_CALLS.clear()
     try:
         _, g0, hinv = emor
         # the adapter parses 'invemor.txt' relative to the CWD, like the reference (linearization_net.py:219)
@@ -169,6 +183,9 @@ def test_patch_reference_modules(shdr_gpu, emor, tmp_path, monkeypatch):
         assert np.abs(seen["w"].numpy() - w_ref).max() <= 1e-5
         ref_out = oracle.increase(oracle.invcrf_pca_w_2_invcrf(seen["w"].numpy(), g0, hinv))
         assert out.shape == (2, 1024) and np.abs(out.numpy() - ref_out).max() <= 5e-6
+
+        # graph mode goes through tf.py_function for every forward and gradient call; eager mode never does
+        assert (len(PY_FUNCTION_CALLS) > 10) == (not eager)
 
         monkeypatch.setenv("SHDR_NATIVE", "0")          # A/B switch leaves the stock ops alone
         assert tf_adapter.patch(lin, tfu) is False
