@@ -163,18 +163,23 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
 #pragma unroll 1
     for (int i = 1; i < PFD; ++i)
       if (pf && r + i < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + i * rs3));
+    // register prefetch TWO rows ahead: n* is the row that enters next, f* the one after it
     float n0 = (xok0 && r < h) ? __ldg(src + off) : -2.0f;     // out of the image: no vote
     float n1 = (xok1 && r < h) ? __ldg(src + off + 3) : -2.0f;
+    float f0 = (xok0 && r + 1 < h) ? __ldg(src + off + rs3) : -2.0f;
+    float f1 = (xok1 && r + 1 < h) ? __ldg(src + off + rs3 + 3) : -2.0f;
     float c0, c1;
-    // one row step: clamp the row loaded during the previous step (NaN -> -2: votes 0, like tf.where on a NaN
-    // compare), start the load of the next row and the L2 prefetch PFD rows ahead
+    // one row step: clamp the row loaded two steps ago (NaN -> -2: votes 0, like tf.where on a NaN compare), start the
+    // load of the row two steps ahead and the L2 prefetch PFD rows ahead
     auto advance = [&]() {
       c0 = fminf(fmaxf(n0, -2.0f), 3.0f);
       c1 = fminf(fmaxf(n1, -2.0f), 3.0f);
+      n0 = f0;
+      n1 = f1;
       off += rs3;
-      const bool rok = r + 1 < h;
-      n0 = (xok0 && rok) ? __ldg(src + off) : -2.0f;
-      n1 = (xok1 && rok) ? __ldg(src + off + 3) : -2.0f;
+      const bool rok = r + 2 < h;
+      f0 = (xok0 && rok) ? __ldg(src + off + rs3) : -2.0f;
+      f1 = (xok1 && rok) ? __ldg(src + off + rs3 + 3) : -2.0f;
       if (pf && r + PFD < h) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + off + pfoff));
     };
     // warm-up: rows y0-7 .. y0+7 enter, nothing leaves, nothing is emitted
