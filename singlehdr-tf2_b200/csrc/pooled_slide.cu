@@ -90,6 +90,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "bra WAIT_%=;\n"
       "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
 }
+// consumers have slack (they wait for the producers ~30 % of the time): after a failed first poll they sleep ~100 ns
+// between polls, so that the polls do not take issue slots from the producer warps of the same scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n"
+      "WAIT_%=:\n\t"
+      "nanosleep.u32 %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n\t}" ::"r"(a), "r"(parity), "r"(100) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -379,7 +394,7 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
         sobel_at(fq + (long long)y * rs3, y == 0 ? rs3 : -rs3, y == p.h - 1 ? -rs3 : rs3, oxm, oxp, fv, fdy, fdx);
       const int ny = min(y + HR, p.h - 1) - max(y - HL, 0) + 1;
       const unsigned s = qq % NST, ph = (qq / NST) & 1u;
-      mbar_wait(bars + s, ph);             // producers filled this stage
+      mbar_wait_backoff(bars + s, ph);     // producers filled this stage
       const int4* vl = reinterpret_cast<const int4*>(myS + s * STAGE_INTS);
       float f[32];
       if (xedge) {                         // the in-bounds count varies along the row: one scale per column
