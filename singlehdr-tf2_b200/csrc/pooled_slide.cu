@@ -20,17 +20,22 @@
 // clamp and the window sum commute with the difference, so the producers slide B + 1 running sums per (column,
 // colour, B) and difference them when a row is emitted.
 //
-// Pipeline (one persistent CTA per SM, 28 warps, tasks = image x 64-column strip x row segment):
-//   producers (16 warps, one thread per (column incl. 7 + 8 halo, colour, {B4 + B8 | B16})):
-//       global -> T (fixed point) -> private 16-row ring in shared memory (the leaving row's T);
-//       S_b += G_b(T_enter) - G_b(T_leave); column vote sums min(S_b - S_{b+1}, 2^28 - 1) -> stage[channel][column]
+// Pipeline (one persistent CTA per SM, 20 warps, tasks = image x 64-column strip x row segment; 15 warm-up rows
+// per task):
+//   producers (8 warps, one thread per (TWO adjacent columns incl. 7 + 8 halo, colour, {B4 + B8 | B16})):
+//       global (register prefetch two rows ahead, L2 prefetch 8 rows ahead) -> T (fixed point) -> private 16-row ring
+//       in shared memory (the leaving row's T); S_b += G_b(T_enter) - G_b(T_leave) (the add / subtract as IMAD on the
+//       fma pipe: the alu pipe, which runs the DPX clamps, is the scarce one); column vote sums S_b - S_{b+1} ->
+//       stage[channel][column] with 64-bit stores
 //   consumers (12 warps = 2 row groups x 3 channel groups x 2 half strips, one LANE PER CHANNEL):
-//       47 column sums -> 32 sliding horizontal sums (exact, < 2^32) -> fp32 -> x 1/(count * 2^24) ->
-//       staging[pixel][channel] (lanes = consecutive channels: conflict-free) -> one cp.async.bulk store per row.
+//       47 column sums -> 32 sliding horizontal sums (exact, < 2^32: one column per window is capped at 2^28 - 1) ->
+//       fp32 -> x 1/(count * 2^24) -> staging[pixel][channel] (lanes = consecutive channels: conflict-free) -> one
+//       cp.async.bulk store per row, staging double-buffered per group (one named barrier per row).
 //   (FULL: each consumer lane also computes img + Sobel of one (pixel, colour) of the row into the staging row.)
-// Hand-off through an mbarrier ring of 4 column-sum stages; the two consumer groups alternate rows.
-// All shared-memory traffic is conflict-free by construction (lanes = consecutive columns or consecutive channels;
-// stage pitch 84 = 20 mod 32 words for the 128-bit loads of 8 consecutive channels).
+// Hand-off through an mbarrier ring of 3 column-sum stages; the two consumer groups alternate rows.
+// All shared-memory traffic is conflict-free by construction (lanes = consecutive column pairs or consecutive
+// channels; stage pitch 84 = 20 mod 32 words for the 128-bit loads of 8 consecutive channels).
+// History, measurements and the experiments that did not pay: profiles/README.md (round 2), DESIGN.md section 4.1.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -161,8 +166,8 @@ __device__ __forceinline__ void producer(const Params& p, int* __restrict__ sS, 
     const bool xok0 = act && gx >= 0 && gx < p.w;
     const bool xok1 = act && gx + 1 >= 0 && gx + 1 < p.w && 2 * cp + 1 < CW;
     const float* src = p.img + ((long long)k.n * h * p.w + gx) * 3 + colour;   // column 2*cp; the next one is src + 3
-    // The register prefetch (one row ahead) only covers an L2 hit; under the write stream a DRAM read takes longer
-    // than a row, so every eighth column also pulls the row PFD rows ahead into L2 (a row of the strip is 948 B).
+    // The register prefetch (two rows ahead) only covers an L2 hit; under the write stream a DRAM read takes longer
+    // than that, so every eighth column also pulls the row PFD rows ahead into L2 (a row of the strip is 948 B).
     const bool pf = xok0 && colour == 0 && ((cp & 3) == 0 || cp == NCP - 1);
 #pragma unroll
     for (int j = 0; j < NG; ++j) { S0[j] = 0; S1[j] = 0; }
@@ -502,6 +507,7 @@ int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool fu
   p.nsy = (h + p.rseg - 1) / p.rseg;
   const long long total = (long long)n * p.nsx * p.nsy;
   SHDR_REQUIRE(total > 0 && total < 0x7fffffffLL, "pool_slide: %lld tasks out of range", total);
+  SHDR_REQUIRE((long long)h * w * 3 < 0x7fffffffLL, "pool_slide: one image of %d x %d exceeds the 32-bit row offsets", h, w);
   p.ntasks = (int)total;
   return full93 ? sl::launch_t<true>(p, sms, st) : sl::launch_t<false>(p, sms, st);
 }
