@@ -107,18 +107,19 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
   if (BF16) {
     // CHP == CH here (93 is odd); the strip base p0 * CH * 2 bytes is 16-byte aligned (p0 is a multiple of 128)
     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)p0 * CH;
-    const int nv = vec_ok ? (nfl >> 3) : 0;               // 8 values = 128 bits
-    uint4* o4 = reinterpret_cast<uint4*>(ob);
+    // consecutive lanes read consecutive 128-bit words of the strip (conflict-free) and write 64 bits each
+    const int nv = vec_ok ? (nfl >> 2) : 0;               // 4 values in, 2 x bf16x2 out
+    const float4* s4 = reinterpret_cast<const float4*>(s);
+    uint2* o2 = reinterpret_cast<uint2*>(ob);
+#pragma unroll 4
     for (int i = tid; i < nv; i += STRIP) {
-      const float* q = s + 8 * i;
-      __nv_bfloat162 a = __floats2bfloat162_rn(q[0], q[1]), b = __floats2bfloat162_rn(q[2], q[3]);
-      __nv_bfloat162 c = __floats2bfloat162_rn(q[4], q[5]), d = __floats2bfloat162_rn(q[6], q[7]);
-      uint4 v;
+      const float4 q = s4[i];
+      __nv_bfloat162 a = __floats2bfloat162_rn(q.x, q.y), b = __floats2bfloat162_rn(q.z, q.w);
+      uint2 v;
       v.x = *reinterpret_cast<unsigned*>(&a); v.y = *reinterpret_cast<unsigned*>(&b);
-      v.z = *reinterpret_cast<unsigned*>(&c); v.w = *reinterpret_cast<unsigned*>(&d);
-      __stcs(o4 + i, v);
+      __stcs(o2 + i, v);
     }
-    for (int i = (nv << 3) + tid; i < nfl; i += STRIP) ob[i] = __float2bfloat16_rn(s[i]);
+    for (int i = (nv << 2) + tid; i < nfl; i += STRIP) ob[i] = __float2bfloat16_rn(s[i]);
     return;
   }
   float* og = out + (size_t)p0 * CH;
