@@ -463,3 +463,15 @@ def test_pooled_sparse_votes_stay_relative(shdr_gpu):
     assert_rel(got, ref, RTOL_POOL)
     assert_rel(got, t64, RTOL_POOL)
     assert ((ref > 0) & (ref < 1e-6)).any()               # the case really contains tiny non-zero pooled values
+
+
+def test_pooled_is_bit_deterministic(shdr_gpu):
+    """The integer pipeline has no floating-point reduction whose order could vary: repeated launches (task order,
+    warp timing and strip assignment differ) must give bit-identical tensors, for both variants."""
+    img = rnd((5, 150, 200, 3), 77)
+    d = shdr_gpu.DeviceArray.from_numpy(img)
+    a84, a93 = shdr_gpu.hist_multi(d, pool=True).numpy(), shdr_gpu.frontend(d, pool=True).numpy()
+    for _ in range(5):
+        assert np.array_equal(shdr_gpu.hist_multi(d, pool=True).numpy(), a84)
+        assert np.array_equal(shdr_gpu.frontend(d, pool=True).numpy(), a93)
+    assert np.array_equal(a93[..., 9:], a84)
