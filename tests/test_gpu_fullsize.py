@@ -104,3 +104,17 @@ def test_pooled_large_frames(shdr_gpu, shape):
     out = shdr_gpu.hist_multi(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
     ref = c_oracle.hist_multi(img, pool_k=16)
     assert np.all(np.abs(out - ref) <= 1e-5 * np.abs(ref))
+
+
+def test_config4p_pooled_frontend_full(shdr_gpu):
+    """8 x 512 x 512 pooled 93-channel front end (one sliding-window launch): img / Sobel slices bit-exact, pooled
+    histograms within 1e-5 pure relative of the C oracle on every element, and equal to the 84-channel kernel."""
+    if not HAVE_C:
+        pytest.skip("C oracle not built")
+    img = rnd((8, 512, 512, 3), 44)
+    d = shdr_gpu.DeviceArray.from_numpy(img)
+    f = shdr_gpu.frontend(d, pool=True).numpy()
+    ref = c_oracle.frontend(img, pool_k=16)
+    assert np.array_equal(f[..., :9], ref[..., :9])
+    assert np.all(np.abs(f[..., 9:] - ref[..., 9:]) <= 1e-5 * np.abs(ref[..., 9:]))
+    assert np.array_equal(f[..., 9:], shdr_gpu.hist_multi(d, pool=True).numpy())
