@@ -327,7 +327,7 @@ template <bool SMEM, bool VEC>
 static int launch_apply_px_t(const float* x, const float* rf, float* y, float* clipped, float* alpha, int b,
                              long long npx, int k, int clip, float thr, cudaStream_t st, int dev, bool pdl) {
   const long long quantum = 4LL * APPLY_THREADS;            // pixels: every thread one group of 4
-  long long per_chunk = quantum * 8;
+  long long per_chunk = quantum * 4;                        // 4096 pixels = 12 K elements per CTA (see launch_apply_t)
   const long long want = (long long)sm_count(dev) * 8;
   while (per_chunk > quantum && (long long)b * ((npx + per_chunk - 1) / per_chunk) < want) per_chunk >>= 1;
   const long long chunks = (npx + per_chunk - 1) / per_chunk;
@@ -368,7 +368,11 @@ static int launch_apply_t(const float* x, const float* rf, float* y, int b, long
                           cudaStream_t st, int dev, bool pdl) {
   // chunk: multiple of 4 * threads * unroll elements; shrink until the grid has >= 8 CTAs per SM
   const long long quantum = 4LL * APPLY_THREADS * APPLY_UNROLL;   // 4096 elements
-  long long per_chunk = quantum * 8;                              // 32768 elements = 128 KB in
+  // 8192 elements per CTA: several waves of short CTAs (the grid of 32 K-element chunks was 1.7 waves: its tail cost
+  // 12 % -- A/B on config 3: 32 K 0.0770 ms, 16 K 0.0731, 8 K 0.0685, 4 K 0.0712)
+  // 8192 elements per CTA: several waves of short CTAs.  The grid of 32 K-element chunks was 1.7 waves and its tail
+  // cost 12 % (A/B on config 3: 32 K 0.0770 ms, 16 K 0.0731, 8 K 0.0685, 4 K 0.0712).
+  long long per_chunk = quantum * 2;
   const long long want = (long long)sm_count(dev) * 8;
   while (per_chunk > quantum && (long long)b * ((n + per_chunk - 1) / per_chunk) < want) per_chunk >>= 1;
   long long chunks = (n + per_chunk - 1) / per_chunk;
@@ -536,7 +540,7 @@ extern "C" int shdr_synth_ldr_f32(const float* hdr, const float* t, const float*
   DeviceGuard g(any);
   if (g.status != SHDR_OK) return g.status;
   const long long quantum = 4LL * APPLY_THREADS;
-  long long per_chunk = quantum * 8;
+  long long per_chunk = quantum * 4;
   const long long want = (long long)sm_count(g.dev) * 8;
   while (per_chunk > quantum && (long long)b * ((pixels_per_item + per_chunk - 1) / per_chunk) < want) per_chunk >>= 1;
   const long long chunks = (pixels_per_item + per_chunk - 1) / per_chunk;
