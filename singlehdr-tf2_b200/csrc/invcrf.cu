@@ -368,8 +368,6 @@ static int launch_apply_t(const float* x, const float* rf, float* y, int b, long
                           cudaStream_t st, int dev, bool pdl) {
   // chunk: multiple of 4 * threads * unroll elements; shrink until the grid has >= 8 CTAs per SM
   const long long quantum = 4LL * APPLY_THREADS * APPLY_UNROLL;   // 4096 elements
-  // 8192 elements per CTA: several waves of short CTAs (the grid of 32 K-element chunks was 1.7 waves: its tail cost
-  // 12 % -- A/B on config 3: 32 K 0.0770 ms, 16 K 0.0731, 8 K 0.0685, 4 K 0.0712)
   // 8192 elements per CTA: several waves of short CTAs.  The grid of 32 K-element chunks was 1.7 waves and its tail
   // cost 12 % (A/B on config 3: 32 K 0.0770 ms, 16 K 0.0731, 8 K 0.0685, 4 K 0.0712).
   long long per_chunk = quantum * 2;
