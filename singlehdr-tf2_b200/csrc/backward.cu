@@ -110,7 +110,7 @@ template <bool NEED_GX, bool NEED_GRF>
 static int launch_apply_bwd_t(const float* x, const float* rf, const float* gy, float* gx, float* grf, int b,
                               long long n, int k, cudaStream_t st, int dev) {
   const long long quantum = 4096;
-  long long per_chunk = quantum * 16;      // 65536 elements per CTA: one flush of k atomics per 64 K elements
+  long long per_chunk = quantum * 2;       // 8192 elements per CTA (one flush of k atomics each): ~3 waves of CTAs
   const long long want = (long long)sm_count(dev) * 4;
   while (per_chunk > quantum && (long long)b * ((n + per_chunk - 1) / per_chunk) < want) per_chunk >>= 1;
   const long long chunks = (n + per_chunk - 1) / per_chunk;
