@@ -91,6 +91,29 @@ int shdr_frontend_f32(const float* img, float* out, int n, int h, int w,
  * changes numerics and is therefore never what the parity-gated default path or bench.py's headline uses. */
 int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h, int w, void* stream);
 
+/* ---- front end fused into the input of crfFeatureNet.conv1 --------------
+ * Replaces  tf.concat([img, edge6, hist4, hist8, hist16], -1)   (linearization_net.py:322)
+ *        ->  crfFeatureNet.conv1 = Conv2D(64, (7,7), strides (2,2), padding 'SAME', bias)
+ *            (linearization_net.py:91,107)
+ * and optionally the inference-mode norm1 + act1 behind it (:108-109) as a per-channel scale / shift / ReLU.
+ * The 93-channel tensor never reaches HBM: each CTA builds the bf16 feature tile of a 16 x 8 block of output
+ * pixels in shared memory and contracts it with the 7x7x93x64 kernel on the tensor cores (tcgen05, fp32
+ * accumulation).  bf16 operands change numerics, so this is a separate entry point and never the parity-gated
+ * fp32 default: against the fp32 convolution of the fp32 features the error is ~3e-3 of the output's scale;
+ * against the same convolution of bf16-rounded features and weights it is fp32 summation-order noise.
+ *
+ * shdr_conv1_pack_weights_f32: kernel_hwio is conv1's variable [7][7][93][64] (device, fp32, the layout Keras
+ * stores); packed receives shdr_conv1_packed_bytes() bytes: bf16, K split into (img, edges, hist4, hist8 | hist16),
+ * each tap an operand image the tensor cores read as is.  Re-pack whenever the weights change.
+ * shdr_frontend_conv1_f32: img [n,h,w,3] -> out [n, ceil(h/2), ceil(w/2), 64] fp32 =
+ *   act((conv) * scale[o] + shift[o]);  scale NULL = 1, shift NULL = 0 (shift = the conv bias for a plain
+ *   conv1; a folded batch norm gives both), relu != 0 applies max(., 0).  h, w >= 2. */
+size_t shdr_conv1_packed_bytes(void);
+int shdr_conv1_pack_weights_f32(const float* kernel_hwio, void* packed, void* stream);
+int shdr_frontend_conv1_f32(const float* img, const void* packed, const float* scale,
+                            const float* shift, int relu, float* out, int n, int h, int w,
+                            void* stream);
+
 /* ---- (B) inverse-CRF stage ----------------------------------------------- */
 
 /* AEInvcrfDecodeNet.invcrf_pca_w_2_invcrf (:231-253): curve[b,1024] = g0 + hinv.w[b,11];

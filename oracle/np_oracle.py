@@ -137,6 +137,46 @@ def frontend(img, bins=BINS, pool_k=0, dtype=np.float32):
         [img, sobel_edges6(img, dtype), hist_multi(img, bins, pool_k, dtype)], axis=-1)
 
 
+def bf16_round(x):
+    """float32 -> bfloat16 (round to nearest even) -> float32: what ``cvt.rn.bf16.f32`` does to finite values."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) & 0xFFFF0000).astype(np.uint32).view(np.float32)
+
+
+def conv2d_same_s2(x, kernel, bias=None, dtype=np.float64):
+    """``tf.keras.layers.Conv2D(filters, (kh, kw), strides=(2, 2), padding='SAME')`` on NHWC ``x`` with an HWIO
+    ``kernel`` -- ``crfFeatureNet.conv1``, linearization_net.py:91,107 (7x7, 93 -> 64, bias).  TF 'SAME':
+    ``out = ceil(in / 2)``, ``pad = max((out - 1) * 2 + k - in, 0)`` with ``pad // 2`` in front and the rest behind,
+    zeros; cross-correlation (no kernel flip).  One matmul per tap, accumulated in ``dtype``."""
+    x = np.asarray(x, dtype=dtype)
+    kernel = np.asarray(kernel, dtype=dtype)
+    n, h, w, c = x.shape
+    kh, kw, ci, co = kernel.shape
+    assert ci == c
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    ph, pw = max((oh - 1) * 2 + kh - h, 0), max((ow - 1) * 2 + kw - w, 0)
+    p = np.pad(x, ((0, 0), (ph // 2, ph - ph // 2), (pw // 2, pw - pw // 2), (0, 0)))
+    out = np.zeros((n, oh, ow, co), dtype)
+    for ky in range(kh):
+        for kx in range(kw):
+            out += p[:, ky:ky + 2 * oh - 1:2, kx:kx + 2 * ow - 1:2, :] @ kernel[ky, kx]
+    if bias is not None:
+        out += np.asarray(bias, dtype)
+    return out
+
+
+def frontend_conv1(img, kernel, bias=None, bf16_operands=False, dtype=np.float64):
+    """``crfFeatureNet.conv1(concat([img, edge6, hist4, hist8, hist16]))``: linearization_net.py:312-322 -> :107.
+    The features are the fp32 ones of :func:`frontend`; ``bf16_operands=True`` rounds features and kernel to bfloat16
+    first (what the fused tensor-core kernel multiplies), the sum is carried in ``dtype``."""
+    feat = frontend(img)
+    kernel = np.asarray(kernel, np.float32)
+    if bf16_operands:
+        feat, kernel = bf16_round(feat), bf16_round(kernel)
+    return conv2d_same_s2(feat, kernel, bias, dtype)
+
+
 # --------------------------------------------------------------------------
 # (B) inverse-CRF stage
 # --------------------------------------------------------------------------

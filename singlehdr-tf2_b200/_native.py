@@ -48,6 +48,9 @@ SIGNATURES = {
     "shdr_hist_multi_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "shdr_frontend_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "shdr_frontend_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "shdr_conv1_packed_bytes": (_sz, []),
+    "shdr_conv1_pack_weights_f32": (_i, [_vp, _vp, _vp]),
+    "shdr_frontend_conv1_f32": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
     "shdr_invcrf_build_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "shdr_increase_f32": (_i, [_vp, _vp, _i, _i, _vp]),
     "shdr_apply_rf_f32": (_i, [_vp, _vp, _vp, _i, _ll, _i, _vp]),

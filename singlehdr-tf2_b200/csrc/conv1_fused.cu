@@ -1,0 +1,381 @@
+// conv1_fused.cu -- SURVEY.md 8(f) rank 2: the feature front end fused into the INPUT of crfFeatureNet.conv1.
+//
+// Reference behaviour restated (ShinYwings/SingleHDR-tf2):
+//   features = tf.concat([img, sobel6, hist4, hist8, hist16], -1)            linearization_net.py:312-322
+//   conv1    = Conv2D(64, (7,7), strides (2,2), padding 'SAME', bias)(features)   linearization_net.py:91,107
+// The 93-channel tensor (372 B per input pixel) is the front end's whole HBM cost and conv1 reduces it 4x
+// spatially right away.  Here it never exists in HBM: every CTA generates the bf16 feature tile of one 16 x 8
+// block of OUTPUT pixels in shared memory and contracts it against the 7x7x93x64 kernel on the tensor cores
+// (tcgen05.mma, bf16 x bf16 -> fp32 accumulators in tensor memory).  HBM traffic: 12 B per input pixel in,
+// 256 B per output pixel (= 64 B per input pixel) out -- the kernel is TENSOR-bound (583 kFLOP per output pixel),
+// unlike everything else in this library.  It changes numerics (bf16 operands, like TF's own bf16/TF32 conv
+// paths; fp32 accumulation) and is therefore a separate entry point, never the parity-gated fp32 default.
+//
+// Implicit GEMM.  D[m, o] = sum_{ky,kx,c} F(2 oy + ky - pt, 2 ox + kx - pl, c) W[ky,kx,c,o];  m = 128 output pixels
+// (16 rows x 8 columns), N = 64 output channels, K = 49 taps x 96 (93 channels + 3 zero).  For one tap the A operand
+// is a SHIFTED, stride-2 VIEW of the feature tile -- no im2col copy is made.  tcgen05 reads K-major operands as
+// 8-row x 16-byte core matrices addressed by (start, LBO, SBO), so the tile is stored as
+//      [input row ly 0..36][column parity px][16-byte channel group cg][q = lx >> 1][8 channels]     (bf16)
+// in which the 8 pixels of one output row of the tile are 8 consecutive q (16 B apart) for every tap:
+//      start = buf + ky RP + (kx & 1) PP + cg CGP + (kx >> 1) 16,   LBO = CGP (next channel group),
+//      SBO = 2 RP (next output row = two input rows down).
+// K is split into two passes of 48 channels (img + edges + hist4 + hist8 + 3 zeros | hist16), each with its own
+// 76 KB feature buffer, so that the CUDA cores generate one pass while the tensor cores consume the other.
+//
+// Roles of the persistent CTA (one per SM, 14 warps): 8 producer warps (one thread per input pixel of the 37 x 21
+// halo tile: Sobel, 28 votes, bf16 pack, six 16-byte shared stores), 1 thread streaming the packed weights (6 KB per
+// tap and pass, 1-D bulk copies into an 8-stage ring), 1 thread issuing the MMAs (3 per tap and pass, 294 per tile),
+// 4 epilogue warps (tcgen05.ld, scale / shift / ReLU, 256 B per output pixel to HBM; two accumulators in tensor
+// memory, so the epilogue of one tile overlaps the MMAs of the next).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace shdr {
+namespace c1 {
+
+using namespace umma;
+
+constexpr int TR = 16, TC = 8;            // output tile (M = 128)
+constexpr int LR = 2 * TR + 5;            // 37 input rows under a tile
+constexpr int LC = 2 * TC + 5;            // 21 input columns
+constexpr int Q = 11;                     // columns per parity plane (even: 11, odd: 10 used)
+constexpr int CG = 6;                     // 16-byte channel groups per pass (48 channels)
+constexpr int CGP = Q * 16;               // 176 B   = LBO of A
+constexpr int PP = CG * CGP;              // 1056 B  parity plane
+constexpr int RP = 2 * PP;                // 2112 B  input row
+constexpr int FBUF = LR * RP;             // 78144 B per pass
+constexpr int SBO_A = 2 * RP;             // 4224 B
+constexpr int NTAP = 49;
+constexpr int KPASS = 48;                 // channels per pass
+constexpr int OC = 64;                    // output channels
+constexpr int WSTAGE = KPASS * OC * 2;    // 6144 B: one tap of one pass
+constexpr int NWS = 8;                    // weight ring depth
+constexpr int NPROD = 256;                // producer threads (warps 0..7)
+constexpr int W_LOAD = 8, W_MMA = 9, W_EPI = 10;
+constexpr int NTHREADS = 14 * 32;
+constexpr int TMEM_COLS = 128;            // two 128 x 64 fp32 accumulators
+constexpr size_t PACKED_BYTES = (size_t)2 * NTAP * WSTAGE;   // 602112
+constexpr int SMEM_BYTES = 2 * FBUF + NWS * WSTAGE;          // 205440
+
+// which of the 93 feature channels sits at K index k of a pass (-1: zero padding)
+__host__ __device__ constexpr int pass_channel(int pass, int k) { return pass == 0 ? (k < 45 ? k : -1) : 45 + k; }
+
+struct Params {
+  const float* img;
+  const unsigned char* wpk;   // packed weights [pass][tap][6144]
+  const float* scale;         // [64] or null (1)
+  const float* shift;         // [64] or null (0): the conv bias, or a folded batch-norm shift
+  float* out;                 // [n, oh, ow, 64]
+  int n, h, w, oh, ow, pt, pl, tiles_y, tiles_x, ntiles, relu;
+};
+
+// ------------------------------------------------------------------------------------------ weight packing
+// kernel [7][7][93][64] fp32 (HWIO, what Keras stores) -> for each pass and tap the B operand image tcgen05 reads:
+// K-major no-swizzle core matrices, [16-channel step][K half][8-channel n group][n row][8 k] bf16 (LBO 1024, SBO 128)
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ kern, __nv_bfloat16* __restrict__ wpk) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= 2 * NTAP * KPASS * OC) return;
+  const int e = i & 7, r = (i >> 3) & 7, ng = (i >> 6) & 7, kh = (i >> 9) & 1;
+  const int rest = i >> 10;                    // (pass * 49 + tap) * 3 + step
+  const int step = rest % 3, pt = rest / 3;
+  const int tap = pt % NTAP, pass = pt / NTAP;
+  const int k = step * 16 + kh * 8 + e, o = ng * 8 + r;
+  const int ch = pass_channel(pass, k);
+  wpk[i] = __float2bfloat16_rn(ch < 0 ? 0.0f : __ldg(kern + ((size_t)tap * SHDR_FRONTEND_CH + ch) * OC + o));
+}
+
+// ------------------------------------------------------------------------------------------ producers
+__device__ __forceinline__ unsigned pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&t);
+}
+template <int NF>
+__device__ __forceinline__ void store_groups(unsigned char* dst, const float* f) {
+#pragma unroll
+  for (int g = 0; g < NF / 8; ++g) {
+    uint4 v;
+    v.x = pack2(f[g * 8 + 0], f[g * 8 + 1]);
+    v.y = pack2(f[g * 8 + 2], f[g * 8 + 3]);
+    v.z = pack2(f[g * 8 + 4], f[g * 8 + 5]);
+    v.w = pack2(f[g * 8 + 6], f[g * 8 + 7]);
+    *reinterpret_cast<uint4*>(dst + g * CGP) = v;
+  }
+}
+
+// one input pixel of pass 0: img (3) | Sobel dy, dx per colour (6) | hist4 (12) | hist8 (24) | 3 zeros
+__device__ __forceinline__ void gen_pass0(const float* __restrict__ img_n, int iy, int ix, int h, int w, unsigned char* dst) {
+  const float* base = img_n + ((size_t)iy * w + ix) * 3;
+  const long long oym = (long long)(reflect1(iy - 1, h) - iy) * w * 3;
+  const long long oyp = (long long)(reflect1(iy + 1, h) - iy) * w * 3;
+  const int oxm = (reflect1(ix - 1, w) - ix) * 3;
+  const int oxp = (reflect1(ix + 1, w) - ix) * 3;
+  float f[KPASS];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* q = base + c;
+    const float v = __ldg(q);
+    const float p00 = __ldg(q + oym + oxm), p01 = __ldg(q + oym), p02 = __ldg(q + oym + oxp);
+    const float p10 = __ldg(q + oxm), p12 = __ldg(q + oxp);
+    const float p20 = __ldg(q + oyp + oxm), p21 = __ldg(q + oyp), p22 = __ldg(q + oyp + oxp);
+    // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to bf16 is the fp32 feature
+    float dy = -p00;
+    dy = __fadd_rn(dy, -2.0f * p01);
+    dy = __fsub_rn(dy, p02);
+    dy = __fadd_rn(dy, p20);
+    dy = __fadd_rn(dy, 2.0f * p21);
+    dy = __fadd_rn(dy, p22);
+    float dx = -p00;
+    dx = __fadd_rn(dx, p02);
+    dx = __fadd_rn(dx, -2.0f * p10);
+    dx = __fadd_rn(dx, 2.0f * p12);
+    dx = __fsub_rn(dx, p20);
+    dx = __fadd_rn(dx, p22);
+    f[c] = v;
+    f[3 + c * 2] = dy;
+    f[4 + c * 2] = dx;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) f[9 + b * 3 + c] = hist_vote_pow2(v, (float)(2 * b + 1) / 8.0f, 4.0f);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) f[21 + b * 3 + c] = hist_vote_pow2(v, (float)(2 * b + 1) / 16.0f, 8.0f);
+  }
+  f[45] = f[46] = f[47] = 0.0f;
+  store_groups<KPASS>(dst, f);
+}
+// pass 1: hist16 (48)
+__device__ __forceinline__ void gen_pass1(const float* __restrict__ img_n, int iy, int ix, int w, unsigned char* dst) {
+  const float* base = img_n + ((size_t)iy * w + ix) * 3;
+  float f[KPASS];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __ldg(base + c);
+#pragma unroll
+    for (int b = 0; b < 16; ++b) f[b * 3 + c] = hist_vote_pow2(v, (float)(2 * b + 1) / 32.0f, 16.0f);
+  }
+  store_groups<KPASS>(dst, f);
+}
+
+struct Tile { int n, oy0, ox0; };
+__device__ __forceinline__ Tile tile_decode(int t, const Params& p) {
+  Tile k;
+  const int per = p.tiles_y * p.tiles_x;
+  k.n = t / per;
+  const int r = t - k.n * per;
+  const int ty = r / p.tiles_x;
+  k.oy0 = ty * TR;
+  k.ox0 = (r - ty * p.tiles_x) * TC;
+  return k;
+}
+
+__device__ void producer(const Params& p, unsigned char* fbuf, uint64_t* ffull, uint64_t* fempty, int tid) {
+  const int lane = tid & 31;
+  unsigned it = 0;
+  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+    const Tile k = tile_decode(t, p);
+    const float* img_n = p.img + (size_t)k.n * p.h * p.w * 3;
+    const int iy0 = 2 * k.oy0 - p.pt, ix0 = 2 * k.ox0 - p.pl;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      unsigned char* fb = fbuf + pass * FBUF;
+      mbar_wait_backoff(fempty + pass, (it & 1) ^ 1);      // the MMAs of the previous tile are done with this buffer
+#pragma unroll 1
+      for (int i = tid; i < LR * LC; i += NPROD) {
+        const int ly = i / LC;
+        const int rr = i - ly * LC;
+        const int px = rr >= Q ? 1 : 0;
+        const int q = rr - px * Q;
+        const int iy = iy0 + ly, ix = ix0 + 2 * q + px;
+        unsigned char* dst = fb + ly * RP + px * PP + q * 16;
+        if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+          if (pass == 0) gen_pass0(img_n, iy, ix, p.h, p.w, dst);
+          else gen_pass1(img_n, iy, ix, p.w, dst);
+        } else {                                           // the convolution's zero padding
+          const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int g = 0; g < CG; ++g) *reinterpret_cast<uint4*>(dst + g * CGP) = z;
+        }
+      }
+      fence_async_smem();                                  // generic-proxy stores -> visible to tcgen05.mma
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ffull + pass);
+    }
+  }
+}
+
+__device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wfull, uint64_t* wempty) {
+  unsigned cnt = 0;
+  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+#pragma unroll 1
+    for (int s = 0; s < 2 * NTAP; ++s, ++cnt) {
+      const unsigned st = cnt % NWS, ph = (cnt / NWS) & 1;
+      mbar_wait(wempty + st, ph ^ 1);
+      mbar_expect_tx(wfull + st, WSTAGE);
+      bulk_load(wbuf + st * WSTAGE, p.wpk + (size_t)s * WSTAGE, WSTAGE, wfull + st);
+    }
+  }
+}
+
+__device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* wbuf, uint64_t* ffull, uint64_t* fempty,
+                           uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty, uint32_t tmem) {
+  constexpr uint32_t IDESC = idesc_bf16_f32(128, OC);
+  const uint32_t fb0 = smem_u32(fbuf), wb0 = smem_u32(wbuf);
+  unsigned cnt = 0, it = 0;
+  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+    const unsigned ab = it & 1, use = it >> 1;
+    mbar_wait(aempty + ab, (use & 1) ^ 1);                 // the epilogue has drained this accumulator
+    fence_after_sync();
+    const uint32_t acc = tmem + ab * OC;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      mbar_wait(ffull + pass, it & 1);
+      fence_after_sync();
+      const uint32_t fb = fb0 + pass * FBUF;
+#pragma unroll 1
+      for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll 1
+        for (int kx = 0; kx < 7; ++kx, ++cnt) {
+          const unsigned st = cnt % NWS, ph = (cnt / NWS) & 1;
+          mbar_wait(wfull + st, ph);
+          fence_after_sync();
+          const uint32_t a0 = fb + ky * RP + (kx & 1) * PP + (kx >> 1) * 16;
+          const uint32_t b0 = wb0 + st * WSTAGE;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const uint64_t ad = smem_desc_nosw(a0 + 2 * c * CGP, CGP, SBO_A);
+            const uint64_t bd = smem_desc_nosw(b0 + c * 2048, 1024, 128);
+            mma_ss(acc, ad, bd, IDESC, (pass | ky | kx | c) ? 1u : 0u);
+          }
+          mma_commit(wempty + st);                          // weight stage free once these MMAs have read it
+        }
+      }
+      mma_commit(fempty + pass);                            // feature buffer free
+    }
+    mma_commit(afull + ab);                                 // accumulator complete
+  }
+}
+
+__device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uint32_t tmem, int wq, int lane) {
+  unsigned it = 0;
+  const int m = wq * 32 + lane;
+  const int r = m >> 3, j = m & 7;
+  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+    const Tile k = tile_decode(t, p);
+    const unsigned ab = it & 1, use = it >> 1;
+    mbar_wait_backoff(afull + ab, use & 1);
+    fence_after_sync();
+    const int oy = k.oy0 + r, ox = k.ox0 + j;
+    const bool ok = oy < p.oh && ox < p.ow;
+    float* o = p.out + (((size_t)k.n * p.oh + oy) * p.ow + ox) * OC;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + ab * OC + half * 32, v);
+      if (half == 1) {                                     // every value of this accumulator is in registers
+        fence_before_sync();
+        mbar_arrive(aempty + ab);
+      }
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int ch = half * 32 + g * 4;
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch));
+          if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch));
+          float4 y;
+          y.x = fmaf(v[g * 4 + 0], sc.x, sh.x);
+          y.y = fmaf(v[g * 4 + 1], sc.y, sh.y);
+          y.z = fmaf(v[g * 4 + 2], sc.z, sh.z);
+          y.w = fmaf(v[g * 4 + 3], sc.w, sh.w);
+          if (p.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+          __stcs(reinterpret_cast<float4*>(o + ch), y);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* fbuf = smem;
+  unsigned char* wbuf = smem + 2 * FBUF;
+  __shared__ uint64_t bars[2 * NWS + 8];
+  __shared__ uint32_t tmem_base;
+  uint64_t* wfull = bars;
+  uint64_t* wempty = bars + NWS;
+  uint64_t* ffull = bars + 2 * NWS;
+  uint64_t* fempty = ffull + 2;
+  uint64_t* afull = ffull + 4;
+  uint64_t* aempty = ffull + 6;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < NWS; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(ffull + s, NPROD / 32);
+      mbar_init(fempty + s, 1);
+      mbar_init(afull + s, 1);
+      mbar_init(aempty + s, 128);
+    }
+    mbar_init_fence();
+  }
+  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(&tmem_base);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base;
+
+  if (warp < W_LOAD) producer(p, fbuf, ffull, fempty, tid);
+  else if (warp == W_LOAD) { if (lane == 0) weight_loader(p, wbuf, wfull, wempty); }
+  else if (warp == W_MMA) { if (lane == 0) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem); }
+  else epilogue(p, afull, aempty, tmem, warp & 3, lane);
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == W_MMA) tmem_free<TMEM_COLS>(tmem);
+}
+
+}  // namespace c1
+}  // namespace shdr
+
+using namespace shdr;
+
+extern "C" size_t shdr_conv1_packed_bytes(void) { return c1::PACKED_BYTES; }
+
+extern "C" int shdr_conv1_pack_weights_f32(const float* kernel_hwio, void* packed, void* stream) {
+  SHDR_REQUIRE(kernel_hwio && packed, "conv1_pack_weights: NULL pointer");
+  SHDR_REQUIRE(aligned16(packed), "conv1_pack_weights: packed must be 16-byte aligned");
+  DeviceGuard g(packed);
+  if (g.status != SHDR_OK) return g.status;
+  const int total = 2 * c1::NTAP * c1::KPASS * c1::OC;
+  c1::k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, (__nv_bfloat16*)packed);
+  SHDR_LAUNCH_CHECK("k_pack_weights");
+  return SHDR_OK;
+}
+
+extern "C" int shdr_frontend_conv1_f32(const float* img, const void* packed, const float* scale, const float* shift,
+                                       int relu, float* out, int n, int h, int w, void* stream) {
+  SHDR_REQUIRE(n >= 0 && h >= 0 && w >= 0, "frontend_conv1: bad shape n=%d h=%d w=%d", n, h, w);
+  if ((long long)n * h * w == 0) return SHDR_OK;
+  SHDR_REQUIRE(img && packed && out, "frontend_conv1: NULL pointer");
+  SHDR_REQUIRE(h >= 2 && w >= 2, "frontend_conv1: REFLECT padding needs h >= 2 and w >= 2 (got %d x %d)", h, w);
+  SHDR_REQUIRE(aligned16(packed) && aligned16(out), "frontend_conv1: packed and out must be 16-byte aligned");
+  SHDR_REQUIRE((!scale || aligned16(scale)) && (!shift || aligned16(shift)), "frontend_conv1: scale / shift must be 16-byte aligned");
+  DeviceGuard g(out);
+  if (g.status != SHDR_OK) return g.status;
+  c1::Params p;
+  p.img = img; p.wpk = (const unsigned char*)packed; p.scale = scale; p.shift = shift; p.out = out;
+  p.n = n; p.h = h; p.w = w; p.relu = relu;
+  // TF 'SAME', stride 2, 7 taps: out = ceil(in / 2), pad = max((out - 1) 2 + 7 - in, 0), the smaller half in front
+  p.oh = (h + 1) / 2; p.ow = (w + 1) / 2;
+  p.pt = ((p.oh - 1) * 2 + 7 - h) / 2; p.pl = ((p.ow - 1) * 2 + 7 - w) / 2;
+  p.tiles_y = (p.oh + c1::TR - 1) / c1::TR; p.tiles_x = (p.ow + c1::TC - 1) / c1::TC;
+  const long long nt = (long long)n * p.tiles_y * p.tiles_x;
+  SHDR_REQUIRE(nt < 0x7fffffffLL && (long long)n * h * w < 0x7fffffffLL, "frontend_conv1: too many pixels for int32 tile indices");
+  p.ntiles = (int)nt;
+  SHDR_CUDA(cudaFuncSetAttribute(c1::k_frontend_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, c1::SMEM_BYTES));
+  const int grid = (int)(nt < sm_count(g.dev) ? nt : sm_count(g.dev));
+  c1::k_frontend_conv1<<<grid, c1::NTHREADS, c1::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  SHDR_LAUNCH_CHECK("k_frontend_conv1");
+  return SHDR_OK;
+}

@@ -93,6 +93,44 @@ def frontend_bf16(img, stream=None):
     return _run_dl(N.lib.shdr_dl_frontend_bf16, [img], stream=stream)
 
 
+def conv1_pack_weights(kernel, stream=None):
+    """Pack ``crfFeatureNet.conv1``'s kernel ``[7,7,93,64]`` (fp32 CUDA tensor, HWIO as Keras stores it,
+    linearization_net.py:91) into the bf16 operand image :func:`frontend_conv1` streams through the tensor cores.
+    Re-pack whenever the variable changes."""
+    (bk,) = _dev_inputs(stream, kernel)
+    if tuple(bk.shape) != (7, 7, N.FRONTEND_CH, 64):
+        raise ValueError(f"conv1_pack_weights: kernel must be [7,7,93,64], got {bk.shape}")
+    out = DeviceArray.empty((int(N.lib.shdr_conv1_packed_bytes()) // 4,), bk.device)
+    N.check(N.lib.shdr_conv1_pack_weights_f32(bk.ptr, out.ptr, _stream(stream)))
+    return out.mark_ready(stream)
+
+
+def frontend_conv1(img, packed, bias=None, scale=None, relu=False, stream=None):
+    """``crfFeatureNet.conv1(tf.concat([img, edge6, hist4, hist8, hist16], -1))`` in ONE kernel
+    (linearization_net.py:312-322 -> :107): ``[n,h,w,3] -> [n, ceil(h/2), ceil(w/2), 64]`` fp32, the 93-channel tensor
+    never touching HBM (tensor cores, bf16 operands, fp32 accumulation -- reduced precision, opt-in).
+    ``packed`` comes from :func:`conv1_pack_weights`; ``bias [64]`` is conv1's bias; ``scale [64]`` / ``relu`` fold an
+    inference-mode ``norm1`` / ``act1`` (:108-109): ``out = act(conv * scale + bias)``."""
+    ins = [img, packed] + [a for a in (scale, bias) if a is not None]
+    bs = _dev_inputs(stream, *ins)
+    bi, bp = bs[0], bs[1]
+    rest = bs[2:]
+    bsc = rest.pop(0) if scale is not None else None
+    bb = rest.pop(0) if bias is not None else None
+    if len(bi.shape) != 4 or bi.shape[3] != 3:
+        raise ValueError(f"frontend_conv1: img must be [n,h,w,3], got {bi.shape}")
+    if int(np.prod(bp.shape, dtype=np.int64)) * 4 != int(N.lib.shdr_conv1_packed_bytes()):
+        raise ValueError("frontend_conv1: `packed` is not the output of conv1_pack_weights")
+    for nm, b_ in (("scale", bsc), ("bias", bb)):
+        if b_ is not None and tuple(b_.shape) != (64,):
+            raise ValueError(f"frontend_conv1: {nm} must be [64], got {b_.shape}")
+    n, h, w, _ = bi.shape
+    out = DeviceArray.empty((n, (h + 1) // 2, (w + 1) // 2, 64), bi.device)
+    N.check(N.lib.shdr_frontend_conv1_f32(bi.ptr, bp.ptr, bsc.ptr if bsc else None, bb.ptr if bb else None,
+                                          1 if relu else 0, out.ptr, n, h, w, _stream(stream)))
+    return out.mark_ready(stream)
+
+
 def hist_multi(img, pool=False, stream=None):
     """``concat([hist4, hist8, hist16], -1)`` -> ``[b,h,w,84]`` in one launch."""
     (b,) = _dev_inputs(stream, img)
