@@ -53,7 +53,7 @@ constexpr int OC = 64;                    // output channels
 constexpr int WSTAGE = KPASS * OC * 2;    // 6144 B: one tap of one pass
 constexpr int NWS = 8;                    // weight ring depth
 constexpr int NPROD = 256;                // producer threads (warps 0..7)
-constexpr int W_LOAD = 8, W_MMA = 9, W_EPI = 10;
+constexpr int W_LOAD = 8, W_MMA = 9;   // warps 10..13: epilogue
 constexpr int NTHREADS = 14 * 32;
 constexpr int TMEM_COLS = 128;            // two 128 x 64 fp32 accumulators
 constexpr size_t PACKED_BYTES = (size_t)2 * NTAP * WSTAGE;   // 602112
@@ -187,7 +187,11 @@ __device__ void producer(const Params& p, unsigned char* fbuf, uint64_t* ffull, 
         const int q = rr - px * Q;
         const int iy = iy0 + ly, ix = ix0 + 2 * q + px;
         unsigned char* dst = fb + ly * RP + px * PP + q * 16;
+#if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 1)   // development A/B only: no feature generation
+        if (i < 0) {
+#else
         if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+#endif
           if (pass == 0) gen_pass0(img_n, iy, ix, p.h, p.w, dst);
           else gen_pass1(img_n, iy, ix, p.w, dst);
         } else {                                           // the convolution's zero padding
@@ -210,16 +214,24 @@ __device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wf
     for (int s = 0; s < 2 * NTAP; ++s, ++cnt) {
       const unsigned st = cnt % NWS, ph = (cnt / NWS) & 1;
       mbar_wait(wempty + st, ph ^ 1);
+#if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 2)   // development A/B only: no weight traffic
+      mbar_arrive(wfull + st);
+#else
       mbar_expect_tx(wfull + st, WSTAGE);
       bulk_load(wbuf + st * WSTAGE, p.wpk + (size_t)s * WSTAGE, WSTAGE, wfull + st);
+#endif
     }
   }
 }
 
+// executed by the WHOLE warp (so that every address stays on the uniform datapath); one elected lane issues
 __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* wbuf, uint64_t* ffull, uint64_t* fempty,
                            uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty, uint32_t tmem) {
   constexpr uint32_t IDESC = idesc_bf16_f32(128, OC);
-  const uint32_t fb0 = smem_u32(fbuf), wb0 = smem_u32(wbuf);
+  const uint64_t ad0 = smem_desc_nosw(smem_u32(fbuf), CGP, SBO_A);
+  const uint64_t bd0 = smem_desc_nosw(smem_u32(wbuf), 1024, 128);
+  const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
+  const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
   unsigned cnt = 0, it = 0;
   for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
     const unsigned ab = it & 1, use = it >> 1;
@@ -230,28 +242,31 @@ __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* 
     for (int pass = 0; pass < 2; ++pass) {
       mbar_wait(ffull + pass, it & 1);
       fence_after_sync();
-      const uint32_t fb = fb0 + pass * FBUF;
 #pragma unroll 1
       for (int ky = 0; ky < 7; ++ky) {
-#pragma unroll 1
+        const uint32_t a_row = a_lo0 + ((pass * FBUF + ky * RP) >> 4);
+#pragma unroll
         for (int kx = 0; kx < 7; ++kx, ++cnt) {
           const unsigned st = cnt % NWS, ph = (cnt / NWS) & 1;
           mbar_wait(wfull + st, ph);
           fence_after_sync();
-          const uint32_t a0 = fb + ky * RP + (kx & 1) * PP + (kx >> 1) * 16;
-          const uint32_t b0 = wb0 + st * WSTAGE;
+          if (elect_one()) {
+            const uint32_t a_lo = a_row + (((kx & 1) * PP + (kx >> 1) * 16) >> 4);
+            const uint32_t b_lo = b_lo0 + st * (WSTAGE >> 4);
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint64_t ad = smem_desc_nosw(a0 + 2 * c * CGP, CGP, SBO_A);
-            const uint64_t bd = smem_desc_nosw(b0 + c * 2048, 1024, 128);
-            mma_ss(acc, ad, bd, IDESC, (pass | ky | kx | c) ? 1u : 0u);
+            for (int c = 0; c < 3; ++c)
+              mma_ss2(acc, a_lo + ((2 * c * CGP) >> 4), a_hi, b_lo + ((c * 2048) >> 4), b_hi, IDESC,
+                      (pass | ky | kx | c) ? 1u : 0u);
+            mma_commit(wempty + st);                        // weight stage free once these MMAs have read it
           }
-          mma_commit(wempty + st);                          // weight stage free once these MMAs have read it
+          __syncwarp();
         }
       }
-      mma_commit(fempty + pass);                            // feature buffer free
+      if (elect_one()) mma_commit(fempty + pass);           // feature buffer free
+      __syncwarp();
     }
-    mma_commit(afull + ab);                                 // accumulator complete
+    if (elect_one()) mma_commit(afull + ab);                // accumulator complete
+    __syncwarp();
   }
 }
 
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) 
 
   if (warp < W_LOAD) producer(p, fbuf, ffull, fempty, tid);
   else if (warp == W_LOAD) { if (lane == 0) weight_loader(p, wbuf, wfull, wempty); }
-  else if (warp == W_MMA) { if (lane == 0) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem); }
+  else if (warp == W_MMA) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem);
   else epilogue(p, afull, aempty, tmem, warp & 3, lane);
 
   fence_before_sync();

@@ -27,16 +27,17 @@ static int b_off(int n, int k) { return (k / 16) * 2048 + ((k / 8) % 2) * B_LBO 
 
 __global__ void __launch_bounds__(128)
 k_test(const uint4* __restrict__ a_img, const uint4* __restrict__ b_img, float* __restrict__ out, int swap, int reps,
-       long long* clk) {
+       long long* clk, int commit_every = 0, int two_acc = 0) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* sA = smem;
   unsigned char* sB = smem + A_BYTES;
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2;   // sink of the intermediate commits
   __shared__ uint32_t tbase;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < A_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = a_img[i];
   for (int i = tid; i < B_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = b_img[i];
-  if (tid == 0) { mbar_init(&bar, 1); mbar_init_fence(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_init_fence(); }
   if (warp == 0) tmem_alloc<64>(&tbase);
   fence_async_smem();
   fence_before_sync();
@@ -52,8 +53,9 @@ k_test(const uint4* __restrict__ a_img, const uint4* __restrict__ b_img, float* 
         const uint32_t aa = smem_u32(sA) + s * 2 * A_LBO, ba = smem_u32(sB) + s * 2048;
         const uint64_t ad = swap ? smem_desc_nosw(aa, A_SBO, A_LBO) : smem_desc_nosw(aa, A_LBO, A_SBO);
         const uint64_t bd = swap ? smem_desc_nosw(ba, B_SBO, B_LBO) : smem_desc_nosw(ba, B_LBO, B_SBO);
-        mma_ss(tm, ad, bd, idesc, (r | s) ? 1u : 0u);
+        mma_ss(tm + ((two_acc && (r & 1)) ? 32u : 0u), ad, bd, idesc, (r | s) ? 1u : 0u);
       }
+      if (commit_every && (r + 1) % commit_every == 0) mma_commit(&bar2);
     }
     mma_commit(&bar);
   }
@@ -126,6 +128,14 @@ int main(int argc, char** argv) {
       cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost);
       printf("%d MMAs (128x64x16, operands in shared memory): %lld clk = %.1f clk / MMA\n", reps * KSTEPS, c,
              (double)c / (reps * KSTEPS));
+    }
+    // does tcgen05.commit cost tensor-pipe time?  one commit (to a sink barrier) after every ce x 3 MMAs
+    for (int ce : {1, 2, 4, 8}) {
+      k_test<<<1, 128, smem>>>(da, db, dout, swap, 512, dclk, ce, 0);
+      cudaDeviceSynchronize();
+      long long c;
+      cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost);
+      printf("commit after every %2d MMAs: %.1f clk / MMA\n", ce * KSTEPS, (double)c / (512 * KSTEPS));
     }
   }
   printf("RESULT %s\n", ok == 1 ? "PASS" : (ok ? "PASS-SWAPPED" : "FAIL"));
