@@ -19,12 +19,13 @@
 // in which the 8 pixels of one output row of the tile are 8 consecutive q (16 B apart) for every tap:
 //      start = buf + ky RP + (kx & 1) PP + cg CGP + (kx >> 1) 16,   LBO = CGP (next channel group),
 //      SBO = 2 RP (next output row = two input rows down).
-// K is split into two passes of 48 channels (img + edges + hist4 + hist8 + 3 zeros | hist16), each with its own
-// 76 KB feature buffer, so that the CUDA cores generate one pass while the tensor cores consume the other.
+// K is split into three passes of 32 channels (channels 0-31 | 32-63 | 64-92 + 3 zeros) that alternate between two
+// 51 KB feature buffers, so that the CUDA cores generate one pass while the tensor cores consume the other.
 //
 // Roles of the persistent CTA (one per SM, 14 warps): 8 producer warps (one thread per input pixel of the 37 x 21
-// halo tile: Sobel, 28 votes, bf16 pack, six 16-byte shared stores), 1 thread streaming the packed weights (6 KB per
-// tap and pass, 1-D bulk copies into an 8-stage ring), 1 thread issuing the MMAs (3 per tap and pass, 294 per tile),
+// halo tile: Sobel / votes of the pass, bf16 pack, four 16-byte shared stores), 1 thread streaming the packed weights
+// (one kernel row of one pass = 28 KB per 1-D bulk copy into a 4-stage ring), 1 warp issuing the MMAs (one elected
+// lane, 14 per kernel row and pass back to back, 294 per tile),
 // 4 epilogue warps (tcgen05.ld, scale / shift / ReLU, 256 B per output pixel to HBM; two accumulators in tensor
 // memory, so the epilogue of one tile overlaps the MMAs of the next).
 #include <cuda_bf16.h>
@@ -41,30 +42,29 @@ constexpr int TR = 16, TC = 8;            // output tile (M = 128)
 constexpr int LR = 2 * TR + 5;            // 37 input rows under a tile
 constexpr int LC = 2 * TC + 5;            // 21 input columns
 constexpr int Q = 11;                     // columns per parity plane (even: 11, odd: 10 used)
-constexpr int CG = 6;                     // 16-byte channel groups per pass (48 channels)
+constexpr int NPASS = 3;                  // K passes per tile
+constexpr int KPASS = 32;                 // channels per pass (96 = 93 + 3 zeros)
+constexpr int CG = KPASS / 8;             // 16-byte channel groups per pass
 constexpr int CGP = Q * 16;               // 176 B   = LBO of A
-constexpr int PP = CG * CGP;              // 1056 B  parity plane
-constexpr int RP = 2 * PP;                // 2112 B  input row
-constexpr int FBUF = LR * RP;             // 78144 B per pass
-constexpr int SBO_A = 2 * RP;             // 4224 B
+constexpr int PP = CG * CGP;              // 704 B   parity plane
+constexpr int RP = 2 * PP;                // 1408 B  input row
+constexpr int FBUF = LR * RP;             // 52096 B per pass
+constexpr int SBO_A = 2 * RP;             // 2816 B
 constexpr int NTAP = 49;
-constexpr int KPASS = 48;                 // channels per pass
 constexpr int OC = 64;                    // output channels
-constexpr int WSTAGE = KPASS * OC * 2;    // 6144 B: one tap of one pass
-constexpr int NWS = 8;                    // weight ring depth
+constexpr int WTAP = KPASS * OC * 2;      // 4096 B: one tap of one pass
+constexpr int WROW = 7 * WTAP;            // 28672 B: one kernel row of one pass = one ring stage
+constexpr int NWS = 4;                    // weight ring depth (kernel rows)
 constexpr int NPROD = 256;                // producer threads (warps 0..7)
-constexpr int W_LOAD = 8, W_MMA = 9;   // warps 10..13: epilogue
+constexpr int W_LOAD = 8, W_MMA = 9;      // warps 10..13: epilogue
 constexpr int NTHREADS = 14 * 32;
 constexpr int TMEM_COLS = 128;            // two 128 x 64 fp32 accumulators
-constexpr size_t PACKED_BYTES = (size_t)2 * NTAP * WSTAGE;   // 602112
-constexpr int SMEM_BYTES = 2 * FBUF + NWS * WSTAGE;          // 205440
-
-// which of the 93 feature channels sits at K index k of a pass (-1: zero padding)
-__host__ __device__ constexpr int pass_channel(int pass, int k) { return pass == 0 ? (k < 45 ? k : -1) : 45 + k; }
+constexpr size_t PACKED_BYTES = (size_t)NPASS * NTAP * WTAP;   // 602112
+constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW;              // 218880
 
 struct Params {
   const float* img;
-  const unsigned char* wpk;   // packed weights [pass][tap][6144]
+  const unsigned char* wpk;   // packed weights [pass][tap][4096]
   const float* scale;         // [64] or null (1)
   const float* shift;         // [64] or null (0): the conv bias, or a folded batch-norm shift
   float* out;                 // [n, oh, ow, 64]
@@ -73,17 +73,16 @@ struct Params {
 
 // ------------------------------------------------------------------------------------------ weight packing
 // kernel [7][7][93][64] fp32 (HWIO, what Keras stores) -> for each pass and tap the B operand image tcgen05 reads:
-// K-major no-swizzle core matrices, [16-channel step][K half][8-channel n group][n row][8 k] bf16 (LBO 1024, SBO 128)
+// K-major no-swizzle core matrices, [16-channel step][K half][8-channel n group][n row][8 k] bf16 (LBO 1024, SBO 128).
+// K index k of pass p is feature channel 32 p + k (zero beyond 92).
 __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ kern, __nv_bfloat16* __restrict__ wpk) {
   const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= 2 * NTAP * KPASS * OC) return;
-  const int e = i & 7, r = (i >> 3) & 7, ng = (i >> 6) & 7, kh = (i >> 9) & 1;
-  const int rest = i >> 10;                    // (pass * 49 + tap) * 3 + step
-  const int step = rest % 3, pt = rest / 3;
-  const int tap = pt % NTAP, pass = pt / NTAP;
-  const int k = step * 16 + kh * 8 + e, o = ng * 8 + r;
-  const int ch = pass_channel(pass, k);
-  wpk[i] = __float2bfloat16_rn(ch < 0 ? 0.0f : __ldg(kern + ((size_t)tap * SHDR_FRONTEND_CH + ch) * OC + o));
+  if (i >= NPASS * NTAP * KPASS * OC) return;
+  const int e = i & 7, r = (i >> 3) & 7, ng = (i >> 6) & 7, kh = (i >> 9) & 1, step = (i >> 10) & 1;
+  const int ptap = i >> 11;                    // pass * 49 + tap
+  const int tap = ptap % NTAP, pass = ptap / NTAP;
+  const int ch = pass * KPASS + step * 16 + kh * 8 + e, o = ng * 8 + r;
+  wpk[i] = __float2bfloat16_rn(ch >= SHDR_FRONTEND_CH ? 0.0f : __ldg(kern + ((size_t)tap * SHDR_FRONTEND_CH + ch) * OC + o));
 }
 
 // ------------------------------------------------------------------------------------------ producers
@@ -91,69 +90,65 @@ __device__ __forceinline__ unsigned pack2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&t);
 }
-template <int NF>
-__device__ __forceinline__ void store_groups(unsigned char* dst, const float* f) {
-#pragma unroll
-  for (int g = 0; g < NF / 8; ++g) {
-    uint4 v;
-    v.x = pack2(f[g * 8 + 0], f[g * 8 + 1]);
-    v.y = pack2(f[g * 8 + 2], f[g * 8 + 3]);
-    v.z = pack2(f[g * 8 + 4], f[g * 8 + 5]);
-    v.w = pack2(f[g * 8 + 6], f[g * 8 + 7]);
-    *reinterpret_cast<uint4*>(dst + g * CGP) = v;
-  }
+
+// feature channel CH (compile-time after unrolling) of a pixel: the concat order of linearization_net.py:322
+//   0-2 img | 3-8 Sobel (c*2 + {dy, dx}) | 9-20 hist4 | 21-44 hist8 | 45-92 hist16 ((bin-1)*3 + c) | 93-95 zero
+__device__ __forceinline__ float feature(int ch, const float* v, const float* sob) {
+  if (ch < 3) return v[ch];
+  if (ch < 9) return sob[ch - 3];
+  if (ch < 21) { const int i = ch - 9;  return hist_vote_pow2(v[i % 3], (float)(2 * (i / 3) + 1) / 8.0f, 4.0f); }
+  if (ch < 45) { const int i = ch - 21; return hist_vote_pow2(v[i % 3], (float)(2 * (i / 3) + 1) / 16.0f, 8.0f); }
+  if (ch < 93) { const int i = ch - 45; return hist_vote_pow2(v[i % 3], (float)(2 * (i / 3) + 1) / 32.0f, 16.0f); }
+  return 0.0f;
 }
 
-// one input pixel of pass 0: img (3) | Sobel dy, dx per colour (6) | hist4 (12) | hist8 (24) | 3 zeros
-__device__ __forceinline__ void gen_pass0(const float* __restrict__ img_n, int iy, int ix, int h, int w, unsigned char* dst) {
+// one input pixel, the 32 channels of pass PASS -> four 16-byte groups of the feature tile
+template <int PASS>
+__device__ __forceinline__ void gen_pixel(const float* __restrict__ img_n, int iy, int ix, int h, int w, unsigned char* dst) {
   const float* base = img_n + ((size_t)iy * w + ix) * 3;
-  const long long oym = (long long)(reflect1(iy - 1, h) - iy) * w * 3;
-  const long long oyp = (long long)(reflect1(iy + 1, h) - iy) * w * 3;
-  const int oxm = (reflect1(ix - 1, w) - ix) * 3;
-  const int oxp = (reflect1(ix + 1, w) - ix) * 3;
-  float f[KPASS];
+  float v[3], sob[6];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float* q = base + c;
-    const float v = __ldg(q);
-    const float p00 = __ldg(q + oym + oxm), p01 = __ldg(q + oym), p02 = __ldg(q + oym + oxp);
-    const float p10 = __ldg(q + oxm), p12 = __ldg(q + oxp);
-    const float p20 = __ldg(q + oyp + oxm), p21 = __ldg(q + oyp), p22 = __ldg(q + oyp + oxp);
-    // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to bf16 is the fp32 feature
-    float dy = -p00;
-    dy = __fadd_rn(dy, -2.0f * p01);
-    dy = __fsub_rn(dy, p02);
-    dy = __fadd_rn(dy, p20);
-    dy = __fadd_rn(dy, 2.0f * p21);
-    dy = __fadd_rn(dy, p22);
-    float dx = -p00;
-    dx = __fadd_rn(dx, p02);
-    dx = __fadd_rn(dx, -2.0f * p10);
-    dx = __fadd_rn(dx, 2.0f * p12);
-    dx = __fsub_rn(dx, p20);
-    dx = __fadd_rn(dx, p22);
-    f[c] = v;
-    f[3 + c * 2] = dy;
-    f[4 + c * 2] = dx;
+  for (int c = 0; c < 3; ++c) v[c] = __ldg(base + c);
+  if (PASS == 0) {
+    const long long oym = (long long)(reflect1(iy - 1, h) - iy) * w * 3;
+    const long long oyp = (long long)(reflect1(iy + 1, h) - iy) * w * 3;
+    const int oxm = (reflect1(ix - 1, w) - ix) * 3;
+    const int oxp = (reflect1(ix + 1, w) - ix) * 3;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) f[9 + b * 3 + c] = hist_vote_pow2(v, (float)(2 * b + 1) / 8.0f, 4.0f);
-#pragma unroll
-    for (int b = 0; b < 8; ++b) f[21 + b * 3 + c] = hist_vote_pow2(v, (float)(2 * b + 1) / 16.0f, 8.0f);
+    for (int c = 0; c < 3; ++c) {
+      const float* q = base + c;
+      const float p00 = __ldg(q + oym + oxm), p01 = __ldg(q + oym), p02 = __ldg(q + oym + oxp);
+      const float p10 = __ldg(q + oxm), p12 = __ldg(q + oxp);
+      const float p20 = __ldg(q + oyp + oxm), p21 = __ldg(q + oyp), p22 = __ldg(q + oyp + oxp);
+      // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to bf16 is the fp32 feature
+      float dy = -p00;
+      dy = __fadd_rn(dy, -2.0f * p01);
+      dy = __fsub_rn(dy, p02);
+      dy = __fadd_rn(dy, p20);
+      dy = __fadd_rn(dy, 2.0f * p21);
+      dy = __fadd_rn(dy, p22);
+      float dx = -p00;
+      dx = __fadd_rn(dx, p02);
+      dx = __fadd_rn(dx, -2.0f * p10);
+      dx = __fadd_rn(dx, 2.0f * p12);
+      dx = __fsub_rn(dx, p20);
+      dx = __fadd_rn(dx, p22);
+      sob[c * 2] = dy;
+      sob[c * 2 + 1] = dx;
+    }
   }
-  f[45] = f[46] = f[47] = 0.0f;
-  store_groups<KPASS>(dst, f);
-}
-// pass 1: hist16 (48)
-__device__ __forceinline__ void gen_pass1(const float* __restrict__ img_n, int iy, int ix, int w, unsigned char* dst) {
-  const float* base = img_n + ((size_t)iy * w + ix) * 3;
-  float f[KPASS];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float v = __ldg(base + c);
+  for (int g = 0; g < CG; ++g) {
+    float f[8];
 #pragma unroll
-    for (int b = 0; b < 16; ++b) f[b * 3 + c] = hist_vote_pow2(v, (float)(2 * b + 1) / 32.0f, 16.0f);
+    for (int e = 0; e < 8; ++e) f[e] = feature(PASS * KPASS + g * 8 + e, v, sob);
+    uint4 o;
+    o.x = pack2(f[0], f[1]);
+    o.y = pack2(f[2], f[3]);
+    o.z = pack2(f[4], f[5]);
+    o.w = pack2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + g * CGP) = o;
   }
-  store_groups<KPASS>(dst, f);
 }
 
 struct Tile { int n, oy0, ox0; };
@@ -168,63 +163,74 @@ __device__ __forceinline__ Tile tile_decode(int t, const Params& p) {
   return k;
 }
 
+template <int PASS>
+__device__ __forceinline__ void gen_pass(const Params& p, const float* __restrict__ img_n, int iy0, int ix0,
+                                         unsigned char* fb, int tid) {
+#pragma unroll 1
+  for (int i = tid; i < LR * LC; i += NPROD) {
+    const int ly = i / LC;
+    const int rr = i - ly * LC;
+    const int px = rr >= Q ? 1 : 0;
+    const int q = rr - px * Q;
+    const int iy = iy0 + ly, ix = ix0 + 2 * q + px;
+    unsigned char* dst = fb + ly * RP + px * PP + q * 16;
+#if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 1)   // development A/B only: no feature generation
+    if (i < 0) {
+#else
+    if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
+#endif
+      gen_pixel<PASS>(img_n, iy, ix, p.h, p.w, dst);
+    } else {                                               // the convolution's zero padding
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int g = 0; g < CG; ++g) *reinterpret_cast<uint4*>(dst + g * CGP) = z;
+    }
+  }
+}
+
 __device__ void producer(const Params& p, unsigned char* fbuf, uint64_t* ffull, uint64_t* fempty, int tid) {
   const int lane = tid & 31;
-  unsigned it = 0;
-  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+  unsigned gp = 0;                                         // running pass number: buffer gp & 1, use (gp >> 1)
+  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     const Tile k = tile_decode(t, p);
     const float* img_n = p.img + (size_t)k.n * p.h * p.w * 3;
     const int iy0 = 2 * k.oy0 - p.pt, ix0 = 2 * k.ox0 - p.pl;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      unsigned char* fb = fbuf + pass * FBUF;
-      mbar_wait_backoff(fempty + pass, (it & 1) ^ 1);      // the MMAs of the previous tile are done with this buffer
-#pragma unroll 1
-      for (int i = tid; i < LR * LC; i += NPROD) {
-        const int ly = i / LC;
-        const int rr = i - ly * LC;
-        const int px = rr >= Q ? 1 : 0;
-        const int q = rr - px * Q;
-        const int iy = iy0 + ly, ix = ix0 + 2 * q + px;
-        unsigned char* dst = fb + ly * RP + px * PP + q * 16;
-#if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 1)   // development A/B only: no feature generation
-        if (i < 0) {
-#else
-        if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
-#endif
-          if (pass == 0) gen_pass0(img_n, iy, ix, p.h, p.w, dst);
-          else gen_pass1(img_n, iy, ix, p.w, dst);
-        } else {                                           // the convolution's zero padding
-          const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-          for (int g = 0; g < CG; ++g) *reinterpret_cast<uint4*>(dst + g * CGP) = z;
-        }
-      }
+    for (int pass = 0; pass < NPASS; ++pass, ++gp) {
+      const unsigned b = gp & 1;
+      unsigned char* fb = fbuf + b * FBUF;
+      mbar_wait_backoff(fempty + b, ((gp >> 1) & 1) ^ 1);  // the MMAs that read this buffer two passes ago are done
+      if (pass == 0) gen_pass<0>(p, img_n, iy0, ix0, fb, tid);
+      else if (pass == 1) gen_pass<1>(p, img_n, iy0, ix0, fb, tid);
+      else gen_pass<2>(p, img_n, iy0, ix0, fb, tid);
       fence_async_smem();                                  // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
-      if (lane == 0) mbar_arrive(ffull + pass);
+      if (lane == 0) mbar_arrive(ffull + b);
     }
   }
 }
 
+// one thread: a whole kernel row (7 taps, 28 KB, contiguous in the packed image) per bulk copy and per barrier
 __device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wfull, uint64_t* wempty) {
-  unsigned cnt = 0;
+  unsigned st = 0, ph = 0;
   for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
 #pragma unroll 1
-    for (int s = 0; s < 2 * NTAP; ++s, ++cnt) {
-      const unsigned st = cnt % NWS, ph = (cnt / NWS) & 1;
+    for (int s = 0; s < NPASS * 7; ++s) {
       mbar_wait(wempty + st, ph ^ 1);
 #if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 2)   // development A/B only: no weight traffic
       mbar_arrive(wfull + st);
 #else
-      mbar_expect_tx(wfull + st, WSTAGE);
-      bulk_load(wbuf + st * WSTAGE, p.wpk + (size_t)s * WSTAGE, WSTAGE, wfull + st);
+      mbar_expect_tx(wfull + st, WROW);
+      bulk_load(wbuf + st * WROW, p.wpk + (size_t)s * WROW, WROW, wfull + st);
 #endif
+      if (++st == NWS) { st = 0; ph ^= 1; }
     }
   }
 }
 
-// executed by the WHOLE warp (so that every address stays on the uniform datapath); one elected lane issues
+// executed by the WHOLE warp (so that every address stays on the uniform datapath); one elected lane issues.  The
+// tensor pipe queues only a few MMAs, so any gap in the issue stream is lost time: one barrier poll and one elected
+// block per kernel ROW (14 MMAs of 128 x 64 x 16 back to back), and the poll for the next row runs under their shadow.
 __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* wbuf, uint64_t* ffull, uint64_t* fempty,
                            uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty, uint32_t tmem) {
   constexpr uint32_t IDESC = idesc_bf16_f32(128, OC);
@@ -232,38 +238,37 @@ __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* 
   const uint64_t bd0 = smem_desc_nosw(smem_u32(wbuf), 1024, 128);
   const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
   const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
-  unsigned cnt = 0, it = 0;
+  unsigned st = 0, ph = 0, it = 0, gp = 0;
   for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
     const unsigned ab = it & 1, use = it >> 1;
     mbar_wait(aempty + ab, (use & 1) ^ 1);                 // the epilogue has drained this accumulator
     fence_after_sync();
     const uint32_t acc = tmem + ab * OC;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-      mbar_wait(ffull + pass, it & 1);
+    for (int pass = 0; pass < NPASS; ++pass, ++gp) {
+      const unsigned fbi = gp & 1;
+      mbar_wait(ffull + fbi, (gp >> 1) & 1);
       fence_after_sync();
 #pragma unroll 1
       for (int ky = 0; ky < 7; ++ky) {
-        const uint32_t a_row = a_lo0 + ((pass * FBUF + ky * RP) >> 4);
+        mbar_wait(wfull + st, ph);
+        fence_after_sync();
+        if (elect_one()) {
+          const uint32_t a_row = a_lo0 + ((fbi * FBUF + ky * RP) >> 4);
+          const uint32_t b_row = b_lo0 + st * (WROW >> 4);
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx, ++cnt) {
-          const unsigned st = cnt % NWS, ph = (cnt / NWS) & 1;
-          mbar_wait(wfull + st, ph);
-          fence_after_sync();
-          if (elect_one()) {
-            const uint32_t a_lo = a_row + (((kx & 1) * PP + (kx >> 1) * 16) >> 4);
-            const uint32_t b_lo = b_lo0 + st * (WSTAGE >> 4);
+          for (int kx = 0; kx < 7; ++kx) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-              mma_ss2(acc, a_lo + ((2 * c * CGP) >> 4), a_hi, b_lo + ((c * 2048) >> 4), b_hi, IDESC,
-                      (pass | ky | kx | c) ? 1u : 0u);
-            mma_commit(wempty + st);                        // weight stage free once these MMAs have read it
+            for (int c = 0; c < KPASS / 16; ++c)
+              mma_ss2(acc, a_row + (((kx & 1) * PP + (kx >> 1) * 16 + 2 * c * CGP) >> 4), a_hi,
+                      b_row + ((kx * WTAP + c * 2048) >> 4), b_hi, IDESC, (pass | ky | kx | c) ? 1u : 0u);
           }
-          __syncwarp();
+          mma_commit(wempty + st);                          // ring stage free once these MMAs have read it
+          if (ky == 6) mma_commit(fempty + fbi);            // ... and the feature buffer after the last row of a pass
         }
+        __syncwarp();
+        if (++st == NWS) { st = 0; ph ^= 1; }
       }
-      if (elect_one()) mma_commit(fempty + pass);           // feature buffer free
-      __syncwarp();
     }
     if (elect_one()) mma_commit(afull + ab);                // accumulator complete
     __syncwarp();
@@ -362,7 +367,7 @@ extern "C" int shdr_conv1_pack_weights_f32(const float* kernel_hwio, void* packe
   SHDR_REQUIRE(aligned16(packed), "conv1_pack_weights: packed must be 16-byte aligned");
   DeviceGuard g(packed);
   if (g.status != SHDR_OK) return g.status;
-  const int total = 2 * c1::NTAP * c1::KPASS * c1::OC;
+  const int total = c1::NPASS * c1::NTAP * c1::KPASS * c1::OC;
   c1::k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, (__nv_bfloat16*)packed);
   SHDR_LAUNCH_CHECK("k_pack_weights");
   return SHDR_OK;

@@ -8,7 +8,9 @@ import shdr
 from shdr import _native as N
 shdr.require_gpu()
 FLOP_PX = 2 * 49 * 93 * 64
-def timeit(fn, reps=20):
+REPS = int(os.environ.get('REPS', '20'))
+def timeit(fn, reps=None):
+    reps = reps or REPS
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

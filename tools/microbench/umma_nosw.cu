@@ -38,7 +38,7 @@ k_test(const uint4* __restrict__ a_img, const uint4* __restrict__ b_img, float* 
   for (int i = tid; i < A_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sA)[i] = a_img[i];
   for (int i = tid; i < B_BYTES / 16; i += 128) reinterpret_cast<uint4*>(sB)[i] = b_img[i];
   if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); mbar_init_fence(); }
-  if (warp == 0) tmem_alloc<64>(&tbase);
+  if (warp == 0) tmem_alloc<128>(&tbase);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -46,18 +46,23 @@ k_test(const uint4* __restrict__ a_img, const uint4* __restrict__ b_img, float* 
   const uint32_t tm = tbase;
   const uint32_t idesc = idesc_bf16_f32(M, N);
   long long t0 = 0, t1 = 0;
-  if (tid == 0) {
+  if (warp == 0) {                       // whole warp, one elected lane issues (descriptors stay on the uniform datapath)
+    const uint64_t ad0 = swap ? smem_desc_nosw(smem_u32(sA), A_SBO, A_LBO) : smem_desc_nosw(smem_u32(sA), A_LBO, A_SBO);
+    const uint64_t bd0 = swap ? smem_desc_nosw(smem_u32(sB), B_SBO, B_LBO) : smem_desc_nosw(smem_u32(sB), B_LBO, B_SBO);
     t0 = clock64();
+#pragma unroll 1
     for (int r = 0; r < reps; ++r) {
-      for (int s = 0; s < KSTEPS; ++s) {
-        const uint32_t aa = smem_u32(sA) + s * 2 * A_LBO, ba = smem_u32(sB) + s * 2048;
-        const uint64_t ad = swap ? smem_desc_nosw(aa, A_SBO, A_LBO) : smem_desc_nosw(aa, A_LBO, A_SBO);
-        const uint64_t bd = swap ? smem_desc_nosw(ba, B_SBO, B_LBO) : smem_desc_nosw(ba, B_LBO, B_SBO);
-        mma_ss(tm + ((two_acc && (r & 1)) ? 32u : 0u), ad, bd, idesc, (r | s) ? 1u : 0u);
+      if (elect_one()) {
+#pragma unroll
+        for (int s = 0; s < KSTEPS; ++s)
+          mma_ss2(tm + ((two_acc && (r & 1)) ? 64u : 0u), (uint32_t)ad0 + ((s * 2 * A_LBO) >> 4), (uint32_t)(ad0 >> 32),
+                  (uint32_t)bd0 + ((s * 2048) >> 4), (uint32_t)(bd0 >> 32), idesc, (r | s) ? 1u : 0u);
+        if (commit_every && ((r + 1) & (commit_every - 1)) == 0) mma_commit(&bar2);
       }
-      if (commit_every && (r + 1) % commit_every == 0) mma_commit(&bar2);
+      __syncwarp();
     }
-    mma_commit(&bar);
+    if (elect_one()) mma_commit(&bar);
+    __syncwarp();
   }
   mbar_wait(&bar, 0);
   if (tid == 0) { t1 = clock64(); clk[0] = t1 - t0; }
@@ -69,7 +74,7 @@ k_test(const uint4* __restrict__ a_img, const uint4* __restrict__ b_img, float* 
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_free<64>(tm);
+  if (warp == 0) tmem_free<128>(tm);
 }
 
 int main(int argc, char** argv) {
@@ -137,6 +142,11 @@ int main(int argc, char** argv) {
       cudaMemcpy(&c, dclk, 8, cudaMemcpyDeviceToHost);
       printf("commit after every %2d MMAs: %.1f clk / MMA\n", ce * KSTEPS, (double)c / (512 * KSTEPS));
     }
+    k_test<<<1, 128, smem>>>(da, db, dout, swap, 512, dclk, 0, 1);
+    cudaDeviceSynchronize();
+    long long c2;
+    cudaMemcpy(&c2, dclk, 8, cudaMemcpyDeviceToHost);
+    printf("two accumulators alternating every 3 MMAs, no commits: %.1f clk / MMA\n", (double)c2 / (512 * KSTEPS));
   }
   printf("RESULT %s\n", ok == 1 ? "PASS" : (ok ? "PASS-SWAPPED" : "FAIL"));
   return ok ? 0 : 2;
