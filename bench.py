@@ -42,6 +42,10 @@ WORKLOADS = {
                 "configs[4]: 3840x2160 frames, front end (93 ch) + inverse-CRF linearize, 8 frames per GPU"),
     "config4p": (8, 512, 512, 384,
                  "93-channel front end with the 16x16 'same' pool fused (one launch), batch 8 x 512x512x3"),
+    "config4c": (8, 512, 512, 76,
+                 "configs[3] first stage: front end fused into crfFeatureNet.conv1 (7x7/2 'SAME', 93 -> 64, bias) on the "
+                 "tensor cores (bf16 operands, fp32 accumulate), batch 8 x 512x512x3 -> [8,256,256,64]; the 93-channel "
+                 "tensor never reaches HBM"),
     "config2u": (32, 512, 512, 348,
                  "soft histogram B={4,8,16} WITHOUT the pool (as the reference ships it), batch 32 x 512x512x3 -> 84 ch"),
 }
@@ -68,6 +72,20 @@ def load_peak():
         except Exception:
             pass
     return 6650.0, "of fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_tensor_peak():
+    """bf16 dense tensor peak (TFLOP/s): the burst figure, for a kernel timed alone."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops"]), "of measured (MEASURED_PEAKS.json bf16_tflops, burst)"
+        except Exception:
+            pass
+    return 1590.0, "of fallback (B200_PROFILING.md 1.59 PFLOP/s)"
+
+
+CONV1_FLOP_PER_OUT_PX = 2 * 7 * 7 * 93 * 64     # algorithmic: the 3 zero-padding channels are not counted
 
 
 def load_traffic(workload):
@@ -287,8 +305,17 @@ def make_workload(torch, N, wl, nb, dev, rank, sh):
     img = torch.rand((nb, h, w, 3), device=dev, dtype=torch.float32, generator=gen)
     wts = (torch.randn((nb, 11), device=dev, generator=gen) * 0.5).contiguous()
     out_ch = {"config1": 93, "config2": 84, "config2u": 84, "config3": 3, "config4": 93, "config4p": 93,
-              "config5": 93}[wl]
-    out = torch.empty((nb, h, w, out_ch), device=dev, dtype=torch.float32)
+              "config5": 93, "config4c": 64}[wl]
+    if wl == "config4c":
+        out = torch.empty((nb, (h + 1) // 2, (w + 1) // 2, 64), device=dev, dtype=torch.float32)
+        kern = (torch.randn((7, 7, 93, 64), device=dev, generator=gen) / 67.5).contiguous()   # Glorot-like scale
+        bias = (torch.randn(64, device=dev, generator=gen) * 0.1).contiguous()
+        packed = torch.empty(N.lib.shdr_conv1_packed_bytes() // 4, device=dev, dtype=torch.float32)
+        N.check(N.lib.shdr_conv1_pack_weights_f32(kern.data_ptr(), packed.data_ptr(), sh))
+        kp, bp = packed.data_ptr(), bias.data_ptr()
+    else:
+        out = torch.empty((nb, h, w, out_ch), device=dev, dtype=torch.float32)
+        kern = bias = packed = None
     lin = torch.empty((nb, h, w, 3), device=dev) if wl in ("config3", "config5") else None
     curve = torch.empty((nb, 1024), device=dev)
     ip, op_, wp, cp = img.data_ptr(), out.data_ptr(), wts.data_ptr(), curve.data_ptr()
@@ -304,10 +331,12 @@ def make_workload(torch, N, wl, nb, dev, rank, sh):
             N.check(N.lib.shdr_frontend_f32(ip, op_, nb, h, w, 0, sh))
         elif wl == "config4p":
             N.check(N.lib.shdr_frontend_f32(ip, op_, nb, h, w, 16, sh))
+        elif wl == "config4c":
+            N.check(N.lib.shdr_frontend_conv1_f32(ip, kp, None, bp, 0, op_, nb, h, w, sh))
         else:
             N.check(N.lib.shdr_frontend_f32(ip, op_, nb, h, w, 0, sh))
             N.check(N.lib.shdr_linearize_f32(ip, wp, lin.data_ptr(), cp, nb, h * w * 3, sh))
-    keep = (img, wts, out, lin, curve)
+    keep = (img, wts, out, lin, curve, kern, bias, packed)
     return step, keep, out_ch
 
 
@@ -352,9 +381,20 @@ def sub_record(torch, dist, N, stream, dev, rank, world, wl, nb, steps, warmup, 
     peak, _ = load_peak()
     del keep
     torch.cuda.empty_cache()
-    return {"metric": "Mpixel/s", "value": world * px / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world,
-            "steps": steps, "ms_per_step": ms_step, "scaling": scaling, "config": config_dict(wl, world, nb),
-            "roofline_frac": px * bpp / (kern_ms * 1e-3) / 1e9 / peak}
+    rec = {"metric": "Mpixel/s", "value": world * px / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world,
+           "steps": steps, "ms_per_step": ms_step, "scaling": scaling, "config": config_dict(wl, world, nb),
+           "roofline_frac": px * bpp / (kern_ms * 1e-3) / 1e9 / peak}
+    if wl == "config4c":       # the one tensor-bound kernel: roofline against the measured bf16 GEMM peak
+        tpeak, tsrc = load_tensor_peak()
+        tfl = nb * ((h + 1) // 2) * ((w + 1) // 2) * CONV1_FLOP_PER_OUT_PX / (kern_ms * 1e-3) / 1e12
+        rec["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+                           "peak_source": tsrc, "dtype": "bf16 operands, f32 accumulate",
+                           "note": "N = 64 output channels: a 128x64x16 MMA reads 6 KB of shared-memory operands for 32 "
+                                   "clocks of math, so the shared-memory read port (128 B/clk) caps this shape at 2/3 "
+                                   "of the tensor peak"}
+        rec["hbm_roofline_frac"] = rec.pop("roofline_frac")
+        rec["input_mpixel_per_s"] = rec["value"]
+    return rec
 
 
 def run_native(args):
@@ -481,6 +521,7 @@ def run_native(args):
         plan = {
             "config3": ("config3", 16, args.steps, "weak"),
             "config4p": ("config4p", 8, args.steps, "weak"),
+            "config4c": ("config4c", 8, args.steps, "weak"),
             "config1": ("config1", 1, args.steps, "weak"),
             "config5_weak": ("config5", 8, k5, "weak"),
             "config5_strong": ("config5", 8 // world, k5, "strong (8 frames in total)"),
@@ -555,10 +596,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="config2", choices=sorted(k for k in WORKLOADS if k != "config4c"))   # config4c: sub-record only
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-sub", action="store_true", help="skip the config5 / config3 / config4p / config1 sub-records")
+    ap.add_argument("--no-sub", action="store_true", help="skip the config5 / config3 / config4p / config4c / config1 sub-records")
     ap.add_argument("--subs", default="", help="comma-separated subset of the sub-records to run (default: all)")
     ap.add_argument("--cpu-warm", action="store_true")
     args = ap.parse_args()

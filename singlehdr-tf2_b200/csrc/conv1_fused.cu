@@ -22,12 +22,12 @@
 // K is split into three passes of 32 channels (channels 0-31 | 32-63 | 64-92 + 3 zeros) that alternate between two
 // 51 KB feature buffers, so that the CUDA cores generate one pass while the tensor cores consume the other.
 //
-// Roles of the persistent CTA (one per SM, 14 warps): 8 producer warps (one thread per input pixel of the 37 x 21
+// Roles of the persistent CTA (one per SM, 15 warps): 8 producer warps (one thread per input pixel of the 37 x 21
 // halo tile: Sobel / votes of the pass, bf16 pack, four 16-byte shared stores), 1 thread streaming the packed weights
-// (one kernel row of one pass = 28 KB per 1-D bulk copy into a 4-stage ring), 1 warp issuing the MMAs (one elected
-// lane, 14 per kernel row and pass back to back, 294 per tile),
-// 4 epilogue warps (tcgen05.ld, scale / shift / ReLU, 256 B per output pixel to HBM; two accumulators in tensor
-// memory, so the epilogue of one tile overlaps the MMAs of the next).
+// (one kernel row of one pass = 28 KB per 1-D bulk copy into a 4-stage ring), 2 warps issuing the MMAs (alternating
+// kernel rows, one elected lane, 14 MMAs per row back to back, 294 per tile),
+// 4 epilogue warps (tcgen05.ld of the two partial accumulators, add, scale / shift / ReLU, 256 B per output pixel to
+// HBM; two tiles' accumulators in tensor memory, so the epilogue of one tile overlaps the MMAs of the next).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -56,9 +56,9 @@ constexpr int WTAP = KPASS * OC * 2;      // 4096 B: one tap of one pass
 constexpr int WROW = 7 * WTAP;            // 28672 B: one kernel row of one pass = one ring stage
 constexpr int NWS = 4;                    // weight ring depth (kernel rows)
 constexpr int NPROD = 256;                // producer threads (warps 0..7)
-constexpr int W_LOAD = 8, W_MMA = 9;      // warps 10..13: epilogue
-constexpr int NTHREADS = 14 * 32;
-constexpr int TMEM_COLS = 128;            // two 128 x 64 fp32 accumulators
+constexpr int W_LOAD = 8, W_MMA = 9;      // warps 9, 10: MMA issuers; warps 11..14: epilogue
+constexpr int NTHREADS = 15 * 32;
+constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer warps x (128 x 64 fp32)
 constexpr size_t PACKED_BYTES = (size_t)NPASS * NTAP * WTAP;   // 602112
 constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW;              // 218880
 
@@ -228,29 +228,36 @@ __device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wf
   }
 }
 
-// executed by the WHOLE warp (so that every address stays on the uniform datapath); one elected lane issues.  The
-// tensor pipe queues only a few MMAs, so any gap in the issue stream is lost time: one barrier poll and one elected
-// block per kernel ROW (14 MMAs of 128 x 64 x 16 back to back), and the poll for the next row runs under their shadow.
+// TWO issuer warps, alternating kernel rows.  Each is executed by the WHOLE warp (so that every address stays on the
+// uniform datapath) and one elected lane issues.  The tensor pipe queues only a few MMAs (a 128 x 64 x 16 MMA lasts
+// ~48 clk), so with one issuer the barrier poll, election and descriptor set-up between two rows (~350 clk) were lost
+// time; with two, one warp prepares its row and blocks at the full queue while the other's 14 MMAs run.  Each warp
+// accumulates ITS rows into its OWN tensor-memory tile (the epilogue adds the two), so the summation order -- and with
+// it every output bit -- does not depend on how the two issue streams interleave.
 __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* wbuf, uint64_t* ffull, uint64_t* fempty,
-                           uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty, uint32_t tmem) {
+                           uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty,
+                           uint32_t tmem, unsigned par) {
   constexpr uint32_t IDESC = idesc_bf16_f32(128, OC);
   const uint64_t ad0 = smem_desc_nosw(smem_u32(fbuf), CGP, SBO_A);
   const uint64_t bd0 = smem_desc_nosw(smem_u32(wbuf), 1024, 128);
   const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
   const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
-  unsigned st = 0, ph = 0, it = 0, gp = 0;
+  unsigned gr = 0, it = 0, gp = 0;                         // running kernel-row / tile / pass numbers
   for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
     const unsigned ab = it & 1, use = it >> 1;
     mbar_wait(aempty + ab, (use & 1) ^ 1);                 // the epilogue has drained this accumulator
     fence_after_sync();
-    const uint32_t acc = tmem + ab * OC;
+    const uint32_t acc = tmem + (ab * 2 + par) * OC;
+    bool first = true;                                     // this warp's first row of the tile zero-initialises its tile
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; ++pass, ++gp) {
       const unsigned fbi = gp & 1;
       mbar_wait(ffull + fbi, (gp >> 1) & 1);
       fence_after_sync();
 #pragma unroll 1
-      for (int ky = 0; ky < 7; ++ky) {
+      for (int ky = 0; ky < 7; ++ky, ++gr) {
+        if ((gr & 1) != par) continue;
+        const unsigned st = gr % NWS, ph = (gr / NWS) & 1;
         mbar_wait(wfull + st, ph);
         fence_after_sync();
         if (elect_one()) {
@@ -261,16 +268,17 @@ __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* 
 #pragma unroll
             for (int c = 0; c < KPASS / 16; ++c)
               mma_ss2(acc, a_row + (((kx & 1) * PP + (kx >> 1) * 16 + 2 * c * CGP) >> 4), a_hi,
-                      b_row + ((kx * WTAP + c * 2048) >> 4), b_hi, IDESC, (pass | ky | kx | c) ? 1u : 0u);
+                      b_row + ((kx * WTAP + c * 2048) >> 4), b_hi, IDESC, (first && (kx | c) == 0) ? 0u : 1u);
           }
           mma_commit(wempty + st);                          // ring stage free once these MMAs have read it
-          if (ky == 6) mma_commit(fempty + fbi);            // ... and the feature buffer after the last row of a pass
         }
+        first = false;
         __syncwarp();
-        if (++st == NWS) { st = 0; ph ^= 1; }
       }
+      if (elect_one()) mma_commit(fempty + fbi);            // this warp's MMAs on the feature buffer are done
+      __syncwarp();
     }
-    if (elect_one()) mma_commit(afull + ab);                // accumulator complete
+    if (elect_one()) mma_commit(afull + ab);                // this warp's share of the accumulator is complete
     __syncwarp();
   }
 }
@@ -289,8 +297,11 @@ __device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uin
     float* o = p.out + (((size_t)k.n * p.oh + oy) * p.ow + ox) * OC;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      float v[32];
-      tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + ab * OC + half * 32, v);
+      float v[32], v2[32];                                 // the two issuer warps' partial sums
+      tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (ab * 2) * OC + half * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (ab * 2 + 1) * OC + half * 32, v2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += v2[i];
       if (half == 1) {                                     // every value of this accumulator is in registers
         fence_before_sync();
         mbar_arrive(aempty + ab);
@@ -333,8 +344,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) 
     for (int s = 0; s < NWS; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(ffull + s, NPROD / 32);
-      mbar_init(fempty + s, 1);
-      mbar_init(afull + s, 1);
+      mbar_init(fempty + s, 2);                            // one commit per issuer warp
+      mbar_init(afull + s, 2);
       mbar_init(aempty + s, 128);
     }
     mbar_init_fence();
@@ -347,7 +358,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) 
 
   if (warp < W_LOAD) producer(p, fbuf, ffull, fempty, tid);
   else if (warp == W_LOAD) { if (lane == 0) weight_loader(p, wbuf, wfull, wempty); }
-  else if (warp == W_MMA) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem);
+  else if (warp <= W_MMA + 1) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem, warp - W_MMA);
   else epilogue(p, afull, aempty, tmem, warp & 3, lane);
 
   fence_before_sync();
