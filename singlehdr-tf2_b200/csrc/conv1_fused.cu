@@ -60,7 +60,10 @@ constexpr int W_LOAD = 8, W_MMA = 9;      // warps 9, 10: MMA issuers; warps 11.
 constexpr int NTHREADS = 15 * 32;
 constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer warps x (128 x 64 fp32)
 constexpr size_t PACKED_BYTES = (size_t)NPASS * NTAP * WTAP;   // 602112
-constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW;              // 218880
+constexpr int RAW_R = LR + 2, RAW_C = LC + 2;  // raw fp32 image tile with the Sobel halo: 39 x 23 pixels
+constexpr int RAWP = RAW_C * 3;           // 69 floats per row (odd: neighbouring rows fall on different banks)
+constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 10768
+constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 229648
 
 struct Params {
   const float* img;
@@ -102,24 +105,20 @@ __device__ __forceinline__ float feature(int ch, const float* v, const float* so
   return 0.0f;
 }
 
-// one input pixel, the 32 channels of pass PASS -> four 16-byte groups of the feature tile
+// one input pixel, the 32 channels of pass PASS -> four 16-byte groups of the feature tile.  `r` points at the pixel
+// in the raw tile (its 3 x 3 neighbourhood is there too, REFLECTed at the image border by the staging step).
 template <int PASS>
-__device__ __forceinline__ void gen_pixel(const float* __restrict__ img_n, int iy, int ix, int h, int w, unsigned char* dst) {
-  const float* base = img_n + ((size_t)iy * w + ix) * 3;
+__device__ __forceinline__ void gen_pixel(const float* __restrict__ r, unsigned char* dst) {
   float v[3], sob[6];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) v[c] = __ldg(base + c);
+  for (int c = 0; c < 3; ++c) v[c] = r[c];
   if (PASS == 0) {
-    const long long oym = (long long)(reflect1(iy - 1, h) - iy) * w * 3;
-    const long long oyp = (long long)(reflect1(iy + 1, h) - iy) * w * 3;
-    const int oxm = (reflect1(ix - 1, w) - ix) * 3;
-    const int oxp = (reflect1(ix + 1, w) - ix) * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float* q = base + c;
-      const float p00 = __ldg(q + oym + oxm), p01 = __ldg(q + oym), p02 = __ldg(q + oym + oxp);
-      const float p10 = __ldg(q + oxm), p12 = __ldg(q + oxp);
-      const float p20 = __ldg(q + oyp + oxm), p21 = __ldg(q + oyp), p22 = __ldg(q + oyp + oxp);
+      const float* q = r + c;
+      const float p00 = q[-RAWP - 3], p01 = q[-RAWP], p02 = q[-RAWP + 3];
+      const float p10 = q[-3], p12 = q[3];
+      const float p20 = q[RAWP - 3], p21 = q[RAWP], p22 = q[RAWP + 3];
       // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to bf16 is the fp32 feature
       float dy = -p00;
       dy = __fadd_rn(dy, -2.0f * p01);
@@ -164,7 +163,7 @@ __device__ __forceinline__ Tile tile_decode(int t, const Params& p) {
 }
 
 template <int PASS>
-__device__ __forceinline__ void gen_pass(const Params& p, const float* __restrict__ img_n, int iy0, int ix0,
+__device__ __forceinline__ void gen_pass(const Params& p, const float* __restrict__ raw, int iy0, int ix0,
                                          unsigned char* fb, int tid) {
 #pragma unroll 1
   for (int i = tid; i < LR * LC; i += NPROD) {
@@ -172,14 +171,15 @@ __device__ __forceinline__ void gen_pass(const Params& p, const float* __restric
     const int rr = i - ly * LC;
     const int px = rr >= Q ? 1 : 0;
     const int q = rr - px * Q;
-    const int iy = iy0 + ly, ix = ix0 + 2 * q + px;
+    const int lx = 2 * q + px;
+    const int iy = iy0 + ly, ix = ix0 + lx;
     unsigned char* dst = fb + ly * RP + px * PP + q * 16;
 #if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 1)   // development A/B only: no feature generation
     if (i < 0) {
 #else
     if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
 #endif
-      gen_pixel<PASS>(img_n, iy, ix, p.h, p.w, dst);
+      gen_pixel<PASS>(raw + (ly + 1) * RAWP + (lx + 1) * 3, dst);
     } else {                                               // the convolution's zero padding
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -188,21 +188,46 @@ __device__ __forceinline__ void gen_pass(const Params& p, const float* __restric
   }
 }
 
-__device__ void producer(const Params& p, unsigned char* fbuf, uint64_t* ffull, uint64_t* fempty, int tid) {
+// the fp32 pixels under the tile plus a 1-pixel ring, read from global memory ONCE per tile (the three passes and the
+// 3 x 3 Sobel windows then read shared memory: global loads at a 12-byte lane stride cost ~5 L1 wavefronts each and
+// the L1 data path is what the tensor cores' operand reads saturate).  Ring pixels that are Sobel neighbours of
+// border pixels hold the REFLECTed pixel (-1 -> 1, n -> n-2); positions further out are never used.
+__device__ __forceinline__ void stage_raw(const Params& p, const float* __restrict__ img_n, int iy0, int ix0,
+                                          float* raw, int tid) {
+#pragma unroll 1
+  for (int i = tid; i < RAW_R * RAW_C; i += NPROD) {
+    const int ry = i / RAW_C, rx = i - ry * RAW_C;
+    int iy = iy0 - 1 + ry, ix = ix0 - 1 + rx;
+    iy = iy < 0 ? -iy : (iy >= p.h ? 2 * p.h - 2 - iy : iy);
+    ix = ix < 0 ? -ix : (ix >= p.w ? 2 * p.w - 2 - ix : ix);
+    iy = min(max(iy, 0), p.h - 1);
+    ix = min(max(ix, 0), p.w - 1);
+    const float* src = img_n + ((size_t)iy * p.w + ix) * 3;
+    float* d = raw + ry * RAWP + rx * 3;
+    d[0] = __ldg(src);
+    d[1] = __ldg(src + 1);
+    d[2] = __ldg(src + 2);
+  }
+}
+
+__device__ void producer(const Params& p, unsigned char* fbuf, float* raw, uint64_t* ffull, uint64_t* fempty, int tid) {
   const int lane = tid & 31;
   unsigned gp = 0;                                         // running pass number: buffer gp & 1, use (gp >> 1)
   for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     const Tile k = tile_decode(t, p);
     const float* img_n = p.img + (size_t)k.n * p.h * p.w * 3;
     const int iy0 = 2 * k.oy0 - p.pt, ix0 = 2 * k.ox0 - p.pl;
+    asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");   // every producer is done reading the previous raw tile
+    stage_raw(p, img_n, iy0, ix0, raw, tid);
+    asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; ++pass, ++gp) {
       const unsigned b = gp & 1;
       unsigned char* fb = fbuf + b * FBUF;
       mbar_wait_backoff(fempty + b, ((gp >> 1) & 1) ^ 1);  // the MMAs that read this buffer two passes ago are done
-      if (pass == 0) gen_pass<0>(p, img_n, iy0, ix0, fb, tid);
-      else if (pass == 1) gen_pass<1>(p, img_n, iy0, ix0, fb, tid);
-      else gen_pass<2>(p, img_n, iy0, ix0, fb, tid);
+      if (pass == 0) gen_pass<0>(p, raw, iy0, ix0, fb, tid);
+      else if (pass == 1) gen_pass<1>(p, raw, iy0, ix0, fb, tid);
+      else gen_pass<2>(p, raw, iy0, ix0, fb, tid);
       fence_async_smem();                                  // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
       if (lane == 0) mbar_arrive(ffull + b);
@@ -330,6 +355,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) 
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* fbuf = smem;
   unsigned char* wbuf = smem + 2 * FBUF;
+  float* raw = reinterpret_cast<float*>(smem + 2 * FBUF + NWS * WROW);
   __shared__ uint64_t bars[2 * NWS + 8];
   __shared__ uint32_t tmem_base;
   uint64_t* wfull = bars;
@@ -356,7 +382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) 
   fence_after_sync();
   const uint32_t tmem = tmem_base;
 
-  if (warp < W_LOAD) producer(p, fbuf, ffull, fempty, tid);
+  if (warp < W_LOAD) producer(p, fbuf, raw, ffull, fempty, tid);
   else if (warp == W_LOAD) { if (lane == 0) weight_loader(p, wbuf, wfull, wempty); }
   else if (warp <= W_MMA + 1) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem, warp - W_MMA);
   else epilogue(p, afull, aempty, tmem, warp & 3, lane);
