@@ -15,9 +15,9 @@
 // (16 rows x 8 columns), N = 64 output channels, K = 49 taps x 96 (93 channels + 3 zero).  For one tap the A operand
 // is a SHIFTED, stride-2 VIEW of the feature tile -- no im2col copy is made.  tcgen05 reads K-major operands as
 // 8-row x 16-byte core matrices addressed by (start, LBO, SBO), so the tile is stored as
-//      [input row ly 0..36][column parity px][16-byte channel group cg][q = lx >> 1][8 channels]     (bf16)
+//      [input row ly 0..36][16-byte channel group cg][column parity px][q = lx >> 1][8 channels]     (bf16)
 // in which the 8 pixels of one output row of the tile are 8 consecutive q (16 B apart) for every tap:
-//      start = buf + ky RP + (kx & 1) PP + cg CGP + (kx >> 1) 16,   LBO = CGP (next channel group),
+//      start = buf + ky RP + cg CGP + (kx & 1) PP + (kx >> 1) 16,   LBO = CGP (next channel group),
 //      SBO = 2 RP (next output row = two input rows down).
 // K is split into three passes of 32 channels (channels 0-31 | 32-63 | 64-92 + 3 zeros) that alternate between two
 // 51 KB feature buffers, so that the CUDA cores generate one pass while the tensor cores consume the other.
@@ -45,11 +45,11 @@ constexpr int Q = 11;                     // columns per parity plane (even: 11,
 constexpr int NPASS = 3;                  // K passes per tile
 constexpr int KPASS = 32;                 // channels per pass (96 = 93 + 3 zeros)
 constexpr int CG = KPASS / 8;             // 16-byte channel groups per pass
-constexpr int CGP = Q * 16;               // 176 B   = LBO of A
-constexpr int PP = CG * CGP;              // 704 B   parity plane
-constexpr int RP = 2 * PP;                // 1408 B  input row
-constexpr int FBUF = LR * RP;             // 52096 B per pass
-constexpr int SBO_A = 2 * RP;             // 2816 B
+constexpr int PP = Q * 16;                // 176 B   odd-column plane starts right behind the 11 even columns
+constexpr int CGP = (2 * Q - 1) * 16;     // 336 B   next channel group = LBO of A (21 columns)
+constexpr int RP = (CG * (2 * Q - 1) + 1) * 16;   // 1360 B input row: 85 x 16 B -- 85 = 21 (mod 8), see gen_pass
+constexpr int FBUF = LR * RP;             // 50320 B per pass
+constexpr int SBO_A = 2 * RP;             // 2720 B
 constexpr int NTAP = 49;
 constexpr int OC = 64;                    // output channels
 constexpr int WTAP = KPASS * OC * 2;      // 4096 B: one tap of one pass
@@ -61,9 +61,10 @@ constexpr int NTHREADS = 15 * 32;
 constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer warps x (128 x 64 fp32)
 constexpr size_t PACKED_BYTES = (size_t)NPASS * NTAP * WTAP;   // 602112
 constexpr int RAW_R = LR + 2, RAW_C = LC + 2;  // raw fp32 image tile with the Sobel halo: 39 x 23 pixels
-constexpr int RAWP = RAW_C * 3;           // 69 floats per row (odd: neighbouring rows fall on different banks)
-constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 10768
-constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 229648
+constexpr int RAWC = 24;                  // raw tile, per row and colour: 12 even columns then 12 odd columns (23 used)
+constexpr int RAWP = 3 * RAWC + 3;        // 75 floats per row: 75 = 11 (mod 32) keeps consecutive rows off each other's banks
+constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 11712
+constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 227040
 
 struct Params {
   const float* img;
@@ -107,18 +108,22 @@ __device__ __forceinline__ float feature(int ch, const float* v, const float* so
 
 // one input pixel, the 32 channels of pass PASS -> four 16-byte groups of the feature tile.  `r` points at the pixel
 // in the raw tile (its 3 x 3 neighbourhood is there too, REFLECTed at the image border by the staging step).
+// raw tile word of column rx (0..22), colour 0, in its row: even columns first, then the odd ones
+__device__ __forceinline__ int raw_col(int rx) { return (rx & 1) * (RAWC / 2) + (rx >> 1); }
+
 template <int PASS>
-__device__ __forceinline__ void gen_pixel(const float* __restrict__ r, unsigned char* dst) {
+__device__ __forceinline__ void gen_pixel(const float* __restrict__ row, int rx, unsigned char* dst) {
+  const int xm = raw_col(rx - 1), x0 = raw_col(rx), xp = raw_col(rx + 1);
   float v[3], sob[6];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) v[c] = r[c];
+  for (int c = 0; c < 3; ++c) v[c] = row[c * RAWC + x0];
   if (PASS == 0) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const float* q = r + c;
-      const float p00 = q[-RAWP - 3], p01 = q[-RAWP], p02 = q[-RAWP + 3];
-      const float p10 = q[-3], p12 = q[3];
-      const float p20 = q[RAWP - 3], p21 = q[RAWP], p22 = q[RAWP + 3];
+      const float* q = row + c * RAWC;
+      const float p00 = q[-RAWP + xm], p01 = q[-RAWP + x0], p02 = q[-RAWP + xp];
+      const float p10 = q[xm], p12 = q[xp];
+      const float p20 = q[RAWP + xm], p21 = q[RAWP + x0], p22 = q[RAWP + xp];
       // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to bf16 is the fp32 feature
       float dy = -p00;
       dy = __fadd_rn(dy, -2.0f * p01);
@@ -173,13 +178,15 @@ __device__ __forceinline__ void gen_pass(const Params& p, const float* __restric
     const int q = rr - px * Q;
     const int lx = 2 * q + px;
     const int iy = iy0 + ly, ix = ix0 + lx;
+    // consecutive items = consecutive 16-byte slots (11 even columns, 10 odd ones, next row 85 = 21 (mod 8) slots on):
+    // every quarter-warp store covers all 32 banks
     unsigned char* dst = fb + ly * RP + px * PP + q * 16;
 #if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 1)   // development A/B only: no feature generation
     if (i < 0) {
 #else
     if (iy >= 0 && iy < p.h && ix >= 0 && ix < p.w) {
 #endif
-      gen_pixel<PASS>(raw + (ly + 1) * RAWP + (lx + 1) * 3, dst);
+      gen_pixel<PASS>(raw + (ly + 1) * RAWP, lx + 1, dst);
     } else {                                               // the convolution's zero padding
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
@@ -203,10 +210,10 @@ __device__ __forceinline__ void stage_raw(const Params& p, const float* __restri
     iy = min(max(iy, 0), p.h - 1);
     ix = min(max(ix, 0), p.w - 1);
     const float* src = img_n + ((size_t)iy * p.w + ix) * 3;
-    float* d = raw + ry * RAWP + rx * 3;
+    float* d = raw + ry * RAWP + raw_col(rx);
     d[0] = __ldg(src);
-    d[1] = __ldg(src + 1);
-    d[2] = __ldg(src + 2);
+    d[RAWC] = __ldg(src + 1);
+    d[2 * RAWC] = __ldg(src + 2);
   }
 }
 
