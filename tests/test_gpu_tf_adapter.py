@@ -191,3 +191,100 @@ def test_patch_reference_modules(shdr_gpu, emor, tmp_path, monkeypatch, eager):
         assert tf_adapter.patch(lin, tfu) is False
     finally:
         sys.modules.pop("tensorflow", None)
+
+
+@pytest.mark.parametrize("eager", [True, False], ids=["eager", "graph"])
+def test_patch_fuse_conv1(shdr_gpu, emor, tmp_path, monkeypatch, eager):
+    """patch(..., fuse_conv1=True): inference calls run front end + conv1 + folded norm1 + act1 as ONE tensor-core
+    kernel on the 3-channel image (linearization_net.py:312-322 -> :107-109); training calls keep the stock layers."""
+    import torch
+    from shdr import tf_adapter
+    tf = _install_fake_tf(eager)
+    tf.convert_to_tensor = lambda v: v
+    tf.zeros = lambda shape, dtype: FakeTFTensor(torch.zeros(shape, device="cuda"))
+    tf.reduce_mean = lambda x, axes, keepdims=False: FakeTFTensor(x._t.mean(dim=tuple(axes), keepdim=keepdims))
+    PY_FUNCTION_CALLS.clear()
+    try:
+        _, g0, hinv = emor
+        cols = [("B =", np.linspace(0, 1, 1024, dtype=np.float32)), ("g0 =", g0)] + \
+               [(f"hinv({i + 1})=", hinv[:, i]) for i in range(11)]
+        lines = []
+        for tag, v in cols:
+            lines.append(tag + " ")
+            lines += ["   ".join(f"{float(t):.9e}" for t in r) for r in v.reshape(256, 4)]
+        (tmp_path / "invemor.txt").write_text("\n".join(lines) + "\n")
+        monkeypatch.chdir(tmp_path)
+
+        rng = np.random.default_rng(5)
+        kern = (rng.normal(0, 1, (7, 7, 93, 64)) / 67.5).astype(np.float32)
+        vec = {k: v.astype(np.float32) for k, v in dict(
+            bias=rng.normal(0, 0.1, 64), gamma=rng.uniform(0.5, 1.5, 64), beta=rng.normal(0, 0.1, 64),
+            mean=rng.normal(0, 0.2, 64), var=rng.uniform(0.5, 2.0, 64)).items()}
+        T = lambda a: FakeTFTensor(torch.from_numpy(np.ascontiguousarray(a)).cuda())   # noqa: E731
+        seen = {}
+        lin = types.ModuleType("linearization_net")
+
+        class crfFeatureNet:     # noqa: N801  (reference spelling; attributes of linearization_net.py:88-99)
+            def __init__(self):
+                self.conv1 = types.SimpleNamespace(kernel=T(kern), bias=T(vec["bias"]), use_bias=True)
+                self.norm1 = types.SimpleNamespace(gamma=T(vec["gamma"]), beta=T(vec["beta"]), moving_mean=T(vec["mean"]),
+                                                   moving_variance=T(vec["var"]), epsilon=1e-3)
+
+                def pool1(x):
+                    seen["act1"] = x
+                    return x
+                self.pool1 = pool1
+                self.res1 = self.res2 = self.res3 = self.res4 = self.res5 = lambda x, training: x
+
+            def call(self, ldr, training="training"):
+                seen["stock_input"] = ldr
+                return FakeTFTensor(ldr._t.mean(dim=(1, 2))[:, :64].contiguous())
+
+            def __call__(self, x, training="training"):
+                return type(self).call(self, x, training)
+
+        class AEInvcrfDecodeNet:   # noqa: N801
+            def invcrf_pca_w_2_invcrf(self, w):
+                raise AssertionError("stock TF path must have been replaced")
+
+        class model:            # noqa: N801
+            def call(self, img, training="training"):
+                raise AssertionError("stock TF path must have been replaced")
+
+            def histogram_layer(self, img, max_bin):
+                raise AssertionError("stock TF path must have been replaced")
+
+            @staticmethod
+            def _increase(rf):
+                raise AssertionError("stock TF path must have been replaced")
+
+        lin.crfFeatureNet, lin.AEInvcrfDecodeNet, lin.model = crfFeatureNet, AEInvcrfDecodeNet, model
+        assert tf_adapter.patch(lin, None, fuse_conv1=True) is True
+
+        img = rng.random((2, 40, 56, 3), dtype=np.float32)
+        proj = rng.normal(0, 0.05, (64, 11)).astype(np.float32)
+        net = lin.model()
+        net.crf_feature_net = crfFeatureNet()
+
+        def ae_invcrf_decode_net(feature):
+            seen["feature"] = feature
+            return lin.AEInvcrfDecodeNet().invcrf_pca_w_2_invcrf(FakeTFTensor(feature._t @ torch.from_numpy(proj).cuda()))
+        net.ae_invcrf_decode_net = ae_invcrf_decode_net
+
+        out = net.call(T(img), training=False)
+        scale = vec["gamma"] / np.sqrt(vec["var"] + np.float32(1e-3))
+        shift = (vec["bias"] - vec["mean"]) * scale + vec["beta"]
+        conv = oracle.frontend_conv1(img, kern, None, bf16_operands=True)
+        ref_act = np.maximum(conv * scale + shift, 0.0)
+        assert "stock_input" not in seen
+        assert seen["act1"].shape == (2, 20, 28, 64)
+        assert np.abs(seen["act1"].numpy() - ref_act).max() <= 4e-5 * np.abs(conv).max()
+        assert np.abs(seen["feature"].numpy() - ref_act.mean(axis=(1, 2))).max() <= 1e-4
+        assert out.shape == (2, 1024)
+
+        net.call(T(img), training=True)                 # training: fp32 front end + the stock (differentiable) layers
+        assert seen["stock_input"].shape == (2, 40, 56, 93)
+        assert np.array_equal(seen["stock_input"].numpy(), oracle.frontend(img))
+        assert (len(PY_FUNCTION_CALLS) > 0) == (not eager)
+    finally:
+        sys.modules.pop("tensorflow", None)
