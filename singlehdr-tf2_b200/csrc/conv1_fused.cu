@@ -55,16 +55,25 @@ constexpr int OC = 64;                    // output channels
 constexpr int WTAP = KPASS * OC * 2;      // 4096 B: one tap of one pass
 constexpr int WROW = 7 * WTAP;            // 28672 B: one kernel row of one pass = one ring stage
 constexpr int NWS = 4;                    // weight ring depth (kernel rows)
+// CTA-pair mode (cta_group::2): each CTA holds 32 of the 64 output channels of B -> half the bytes per stage, twice the depth
+template <bool PAIR> struct Ring {
+  static constexpr int TAP = PAIR ? WTAP / 2 : WTAP;      // bytes of one tap in a stage
+  static constexpr int ROW = 7 * TAP;                     // bytes of a stage (one kernel row of one pass)
+  static constexpr int DEPTH = PAIR ? 2 * NWS : NWS;      // both: 114688 B of ring
+  static constexpr int KSTEP = TAP / 2;                   // bytes of one 16-channel step of a tap
+  static constexpr int LBO = KSTEP / 2;                   // K half
+};
 constexpr int NPROD = 256;                // producer threads (warps 0..7)
 constexpr int W_LOAD = 8, W_MMA = 9;      // warps 9, 10: MMA issuers; warps 11..14: epilogue
 constexpr int NTHREADS = 15 * 32;
 constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer warps x (128 x 64 fp32)
-constexpr size_t PACKED_BYTES = (size_t)NPASS * NTAP * WTAP;   // 602112
+constexpr size_t PACKED_ONE = (size_t)NPASS * NTAP * WTAP;     // 602112: one operand image of the whole kernel
+constexpr size_t PACKED_BYTES = 2 * PACKED_ONE;                // the single-CTA image, then the CTA-pair image
 constexpr int RAW_R = LR + 2, RAW_C = LC + 2;  // raw fp32 image tile with the Sobel halo: 39 x 23 pixels
 constexpr int RAWC = 24;                  // raw tile, per row and colour: 12 even columns then 12 odd columns (23 used)
 constexpr int RAWP = 3 * RAWC + 3;        // 75 floats per row: 75 = 11 (mod 32) keeps consecutive rows off each other's banks
 constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 11712
-constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 227040
+constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 227040 (both modes: Ring::DEPTH * Ring::ROW == NWS * WROW)
 
 struct Params {
   const float* img;
@@ -87,6 +96,20 @@ __global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ 
   const int tap = ptap % NTAP, pass = ptap / NTAP;
   const int ch = pass * KPASS + step * 16 + kh * 8 + e, o = ng * 8 + r;
   wpk[i] = __float2bfloat16_rn(ch >= SHDR_FRONTEND_CH ? 0.0f : __ldg(kern + ((size_t)tap * SHDR_FRONTEND_CH + ch) * OC + o));
+}
+// the same for CTA pairs: [pass][kernel row][half of the output channels][kx][16-channel step][K half][4 n groups][n row][8 k]
+// -- each CTA's share of a kernel row is one contiguous 14 KB block (LBO 512, SBO 128)
+__global__ void __launch_bounds__(256) k_pack_weights_pair(const float* __restrict__ kern, __nv_bfloat16* __restrict__ wpk) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= NPASS * NTAP * KPASS * OC) return;
+  const int e = i & 7, r = (i >> 3) & 7, ng = (i >> 6) & 3, kh = (i >> 8) & 1, step = (i >> 9) & 1;
+  int rest = i >> 10;                          // ((pass * 7 + ky) * 2 + half) * 7 + kx
+  const int kx = rest % 7; rest /= 7;
+  const int half = rest & 1; rest >>= 1;
+  const int ky = rest % 7, pass = rest / 7;
+  const int ch = pass * KPASS + step * 16 + kh * 8 + e, o = half * 32 + ng * 8 + r;
+  wpk[i] = __float2bfloat16_rn(ch >= SHDR_FRONTEND_CH ? 0.0f
+                               : __ldg(kern + ((size_t)(ky * 7 + kx) * SHDR_FRONTEND_CH + ch) * OC + o));
 }
 
 // ------------------------------------------------------------------------------------------ producers
@@ -217,45 +240,81 @@ __device__ __forceinline__ void stage_raw(const Params& p, const float* __restri
   }
 }
 
-__device__ void producer(const Params& p, unsigned char* fbuf, float* raw, uint64_t* ffull, uint64_t* fempty, int tid) {
+// Tiles of this CTA: t = blockIdx.x + i * gridDim.x.  In pair mode both CTAs of a cluster must run the same number of
+// iterations (the leader's MMAs drive both), so every role loops over base = t - rank, and a CTA whose own tile index
+// falls off the end runs a dummy tile (no image loads, no stores).
+#define SHDR_FOR_TILES(base, rank) for (int base = (int)blockIdx.x - (int)(rank); base < p.ntiles; base += (int)gridDim.x)
+
+template <bool PAIR>
+__device__ void producer(const Params& p, unsigned char* fbuf, float* raw, uint64_t* ffull, uint64_t* fempty, int tid,
+                         unsigned rank) {
   const int lane = tid & 31;
+  const uint32_t ffull_leader = PAIR ? map_to_rank(ffull, 0) : 0;   // pair mode: both CTAs' producers report to the leader
   unsigned gp = 0;                                         // running pass number: buffer gp & 1, use (gp >> 1)
-  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-    const Tile k = tile_decode(t, p);
-    const float* img_n = p.img + (size_t)k.n * p.h * p.w * 3;
-    const int iy0 = 2 * k.oy0 - p.pt, ix0 = 2 * k.ox0 - p.pl;
-    asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");   // every producer is done reading the previous raw tile
-    stage_raw(p, img_n, iy0, ix0, raw, tid);
-    asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+  SHDR_FOR_TILES(base, rank) {
+    const int t = base + (int)rank;
+    const bool valid = t < p.ntiles;
+    int iy0 = 0, ix0 = 0;
+    if (valid) {
+      const Tile k = tile_decode(t, p);
+      const float* img_n = p.img + (size_t)k.n * p.h * p.w * 3;
+      iy0 = 2 * k.oy0 - p.pt; ix0 = 2 * k.ox0 - p.pl;
+      asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");   // every producer is done reading the previous raw tile
+      stage_raw(p, img_n, iy0, ix0, raw, tid);
+      asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+    }
 #pragma unroll 1
     for (int pass = 0; pass < NPASS; ++pass, ++gp) {
       const unsigned b = gp & 1;
       unsigned char* fb = fbuf + b * FBUF;
       mbar_wait_backoff(fempty + b, ((gp >> 1) & 1) ^ 1);  // the MMAs that read this buffer two passes ago are done
-      if (pass == 0) gen_pass<0>(p, raw, iy0, ix0, fb, tid);
-      else if (pass == 1) gen_pass<1>(p, raw, iy0, ix0, fb, tid);
-      else gen_pass<2>(p, raw, iy0, ix0, fb, tid);
+      if (valid) {
+        if (pass == 0) gen_pass<0>(p, raw, iy0, ix0, fb, tid);
+        else if (pass == 1) gen_pass<1>(p, raw, iy0, ix0, fb, tid);
+        else gen_pass<2>(p, raw, iy0, ix0, fb, tid);
+      }
       fence_async_smem();                                  // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
-      if (lane == 0) mbar_arrive(ffull + b);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(ffull_leader + b * 8);
+        else mbar_arrive(ffull + b);
+      }
     }
   }
 }
 
-// one thread: a whole kernel row (7 taps, 28 KB, contiguous in the packed image) per bulk copy and per barrier
-__device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wfull, uint64_t* wempty) {
+// one thread: a whole kernel row of a pass (7 taps; 28 KB, or this CTA's 14 KB half of the output channels in pair
+// mode -- contiguous in the packed image) per bulk copy and per barrier
+template <bool PAIR>
+__device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wfull, uint64_t* wempty, unsigned rank) {
+  using R = Ring<PAIR>;
   unsigned st = 0, ph = 0;
-  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+  SHDR_FOR_TILES(base, rank) {
 #pragma unroll 1
     for (int s = 0; s < NPASS * 7; ++s) {
       mbar_wait(wempty + st, ph ^ 1);
 #if defined(SHDR_C1_DBG) && (SHDR_C1_DBG & 2)   // development A/B only: no weight traffic
       mbar_arrive(wfull + st);
 #else
-      mbar_expect_tx(wfull + st, WROW);
-      bulk_load(wbuf + st * WROW, p.wpk + (size_t)s * WROW, WROW, wfull + st);
+      mbar_expect_tx(wfull + st, R::ROW);
+      bulk_load(wbuf + st * R::ROW, p.wpk + (size_t)(PAIR ? s * 2 + (int)rank : s) * R::ROW, R::ROW, wfull + st);
 #endif
-      if (++st == NWS) { st = 0; ph ^= 1; }
+      if (++st == R::DEPTH) { st = 0; ph ^= 1; }
+    }
+  }
+}
+
+// pair mode, CTA 1, one thread: tells the leader when this CTA's half of a ring stage has landed
+__device__ void weight_relay(const Params& p, uint64_t* wfull, unsigned rank) {
+  using R = Ring<true>;
+  const uint32_t wfull_leader = map_to_rank(wfull, 0);
+  unsigned st = 0, ph = 0;
+  SHDR_FOR_TILES(base, rank) {
+#pragma unroll 1
+    for (int s = 0; s < NPASS * 7; ++s) {
+      mbar_wait(wfull + st, ph);
+      mbar_arrive_cluster(wfull_leader + st * 8);
+      if (++st == R::DEPTH) { st = 0; ph ^= 1; }
     }
   }
 }
@@ -266,18 +325,26 @@ __device__ void weight_loader(const Params& p, unsigned char* wbuf, uint64_t* wf
 // time; with two, one warp prepares its row and blocks at the full queue while the other's 14 MMAs run.  Each warp
 // accumulates ITS rows into its OWN tensor-memory tile (the epilogue adds the two), so the summation order -- and with
 // it every output bit -- does not depend on how the two issue streams interleave.
+// Pair mode: only the even CTA of the cluster runs this; every MMA is M = 256 (this CTA's tile and the peer's), B is
+// read half from each CTA, and every commit arrives on the barriers of both CTAs.  The barriers that the PEER's threads
+// arrive on (release at cluster scope, after their proxy fence) are waited for with the plain CTA-scope try_wait: this
+// thread never reads the peer's data itself -- the tensor core does, in the peer's SM -- and an acquire at cluster
+// scope compiles to CCTL.IVALL, which waits for every bulk copy in flight (measured: 0.43 ms instead of 0.25).
+template <bool PAIR>
 __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* wbuf, uint64_t* ffull, uint64_t* fempty,
                            uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty,
                            uint32_t tmem, unsigned par) {
-  constexpr uint32_t IDESC = idesc_bf16_f32(128, OC);
+  using R = Ring<PAIR>;
+  constexpr uint32_t IDESC = idesc_bf16_f32(PAIR ? 256 : 128, OC);
   const uint64_t ad0 = smem_desc_nosw(smem_u32(fbuf), CGP, SBO_A);
-  const uint64_t bd0 = smem_desc_nosw(smem_u32(wbuf), 1024, 128);
+  const uint64_t bd0 = smem_desc_nosw(smem_u32(wbuf), R::LBO, 128);
   const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
   const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
   unsigned gr = 0, it = 0, gp = 0;                         // running kernel-row / tile / pass numbers
-  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+  SHDR_FOR_TILES(base, 0) {
     const unsigned ab = it & 1, use = it >> 1;
-    mbar_wait(aempty + ab, (use & 1) ^ 1);                 // the epilogue has drained this accumulator
+    // the epilogue(s) have drained this accumulator
+    mbar_wait(aempty + ab, (use & 1) ^ 1);
     fence_after_sync();
     const uint32_t acc = tmem + (ab * 2 + par) * OC;
     bool first = true;                                     // this warp's first row of the tile zero-initialises its tile
@@ -289,43 +356,59 @@ __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* 
 #pragma unroll 1
       for (int ky = 0; ky < 7; ++ky, ++gr) {
         if ((gr & 1) != par) continue;
-        const unsigned st = gr % NWS, ph = (gr / NWS) & 1;
+        const unsigned st = gr % R::DEPTH, ph = (gr / R::DEPTH) & 1;
         mbar_wait(wfull + st, ph);
         fence_after_sync();
         if (elect_one()) {
           const uint32_t a_row = a_lo0 + ((fbi * FBUF + ky * RP) >> 4);
-          const uint32_t b_row = b_lo0 + st * (WROW >> 4);
+          const uint32_t b_row = b_lo0 + st * (R::ROW >> 4);
 #pragma unroll
           for (int kx = 0; kx < 7; ++kx) {
 #pragma unroll
-            for (int c = 0; c < KPASS / 16; ++c)
-              mma_ss2(acc, a_row + (((kx & 1) * PP + (kx >> 1) * 16 + 2 * c * CGP) >> 4), a_hi,
-                      b_row + ((kx * WTAP + c * 2048) >> 4), b_hi, IDESC, (first && (kx | c) == 0) ? 0u : 1u);
+            for (int c = 0; c < KPASS / 16; ++c) {
+              const uint32_t a_lo = a_row + (((kx & 1) * PP + (kx >> 1) * 16 + 2 * c * CGP) >> 4);
+              const uint32_t b_lo = b_row + ((kx * R::TAP + c * R::KSTEP) >> 4);
+              const uint32_t accum = (first && (kx | c) == 0) ? 0u : 1u;
+              if (PAIR) mma_ss2_pair(acc, a_lo, a_hi, b_lo, b_hi, IDESC, accum);
+              else mma_ss2(acc, a_lo, a_hi, b_lo, b_hi, IDESC, accum);
+            }
           }
-          mma_commit(wempty + st);                          // ring stage free once these MMAs have read it
+          // ring stage free once these MMAs have read it
+          if (PAIR) mma_commit_pair(wempty + st); else mma_commit(wempty + st);
         }
         first = false;
         __syncwarp();
       }
-      if (elect_one()) mma_commit(fempty + fbi);            // this warp's MMAs on the feature buffer are done
+      if (elect_one()) {                                    // this warp's MMAs on the feature buffer are done
+        if (PAIR) mma_commit_pair(fempty + fbi); else mma_commit(fempty + fbi);
+      }
       __syncwarp();
     }
-    if (elect_one()) mma_commit(afull + ab);                // this warp's share of the accumulator is complete
+    if (elect_one()) {                                      // this warp's share of the accumulator is complete
+      if (PAIR) mma_commit_pair(afull + ab); else mma_commit(afull + ab);
+    }
     __syncwarp();
+    ++it;
   }
 }
 
-__device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uint32_t tmem, int wq, int lane) {
+template <bool PAIR>
+__device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uint32_t tmem, int wq, int lane, unsigned rank) {
   unsigned it = 0;
   const int m = wq * 32 + lane;
   const int r = m >> 3, j = m & 7;
-  for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-    const Tile k = tile_decode(t, p);
+  const uint32_t aempty_leader = PAIR ? map_to_rank(aempty, 0) : 0;
+  SHDR_FOR_TILES(base, rank) {
+    const int t = base + (int)rank;
+    const bool valid = t < p.ntiles;
+    Tile k = {0, 0, 0};
+    if (valid) k = tile_decode(t, p);
     const unsigned ab = it & 1, use = it >> 1;
+    ++it;
     mbar_wait_backoff(afull + ab, use & 1);
     fence_after_sync();
     const int oy = k.oy0 + r, ox = k.ox0 + j;
-    const bool ok = oy < p.oh && ox < p.ow;
+    const bool ok = valid && oy < p.oh && ox < p.ow;
     float* o = p.out + (((size_t)k.n * p.oh + oy) * p.ow + ox) * OC;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -336,7 +419,8 @@ __device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uin
       for (int i = 0; i < 32; ++i) v[i] += v2[i];
       if (half == 1) {                                     // every value of this accumulator is in registers
         fence_before_sync();
-        mbar_arrive(aempty + ab);
+        if (PAIR) mbar_arrive_cluster(aempty_leader + ab * 8);
+        else mbar_arrive(aempty + ab);
       }
       if (ok) {
 #pragma unroll
@@ -358,45 +442,64 @@ __device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uin
   }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) {
+template <bool PAIR>
+__device__ __forceinline__ void conv1_body(const Params& p) {
+  using R = Ring<PAIR>;
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* fbuf = smem;
   unsigned char* wbuf = smem + 2 * FBUF;
-  float* raw = reinterpret_cast<float*>(smem + 2 * FBUF + NWS * WROW);
-  __shared__ uint64_t bars[2 * NWS + 8];
+  float* raw = reinterpret_cast<float*>(smem + 2 * FBUF + R::DEPTH * R::ROW);
+  __shared__ uint64_t bars[2 * Ring<true>::DEPTH + 8];
   __shared__ uint32_t tmem_base;
   uint64_t* wfull = bars;
-  uint64_t* wempty = bars + NWS;
-  uint64_t* ffull = bars + 2 * NWS;
+  uint64_t* wempty = bars + R::DEPTH;
+  uint64_t* ffull = bars + 2 * R::DEPTH;
   uint64_t* fempty = ffull + 2;
   uint64_t* afull = ffull + 4;
   uint64_t* aempty = ffull + 6;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned rank = PAIR ? cluster_ctarank() : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < NWS; ++s) { mbar_init(wfull + s, 1); mbar_init(wempty + s, 1); }
+    for (int s = 0; s < R::DEPTH; ++s) {
+      mbar_init(wfull + s, (PAIR && rank == 0) ? 2 : 1);   // leader: its own copy + the peer's relay
+      mbar_init(wempty + s, 1);
+    }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(ffull + s, NPROD / 32);
+      mbar_init(ffull + s, (PAIR ? 2 : 1) * (NPROD / 32)); // pair mode: the producer warps of both CTAs
       mbar_init(fempty + s, 2);                            // one commit per issuer warp
       mbar_init(afull + s, 2);
-      mbar_init(aempty + s, 128);
+      mbar_init(aempty + s, (PAIR ? 2 : 1) * 128);         // pair mode: the epilogue threads of both CTAs
     }
     mbar_init_fence();
   }
-  if (warp == W_MMA) tmem_alloc<TMEM_COLS>(&tmem_base);
+  if (warp == W_MMA) {
+    if (PAIR) tmem_alloc_pair<TMEM_COLS>(&tmem_base); else tmem_alloc<TMEM_COLS>(&tmem_base);
+  }
   fence_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base;
 
-  if (warp < W_LOAD) producer(p, fbuf, raw, ffull, fempty, tid);
-  else if (warp == W_LOAD) { if (lane == 0) weight_loader(p, wbuf, wfull, wempty); }
-  else if (warp <= W_MMA + 1) mma_issuer(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem, warp - W_MMA);
-  else epilogue(p, afull, aempty, tmem, warp & 3, lane);
+  if (warp < W_LOAD) producer<PAIR>(p, fbuf, raw, ffull, fempty, tid, rank);
+  else if (warp == W_LOAD) { if (lane == 0) weight_loader<PAIR>(p, wbuf, wfull, wempty, rank); __syncwarp(); }
+  else if (warp <= W_MMA + 1) {
+    if (!PAIR || rank == 0) mma_issuer<PAIR>(p, fbuf, wbuf, ffull, fempty, wfull, wempty, afull, aempty, tmem, warp - W_MMA);
+    else if (warp == W_MMA) { if (lane == 0) weight_relay(p, wfull, rank); __syncwarp(); }
+  }
+  else epilogue<PAIR>(p, afull, aempty, tmem, warp & 3, lane, rank);
 
   fence_before_sync();
-  __syncthreads();
-  if (warp == W_MMA) tmem_free<TMEM_COLS>(tmem);
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == W_MMA) {
+    if (PAIR) tmem_free_pair<TMEM_COLS>(tmem); else tmem_free<TMEM_COLS>(tmem);
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) { conv1_body<false>(p); }
+// CTA pairs: the two CTAs of a cluster sit on the two SMs of one TPC and share every MMA (cta_group::2)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_frontend_conv1_pair(const Params p) {
+  conv1_body<true>(p);
 }
 
 }  // namespace c1
@@ -414,6 +517,9 @@ extern "C" int shdr_conv1_pack_weights_f32(const float* kernel_hwio, void* packe
   const int total = c1::NPASS * c1::NTAP * c1::KPASS * c1::OC;
   c1::k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, (__nv_bfloat16*)packed);
   SHDR_LAUNCH_CHECK("k_pack_weights");
+  c1::k_pack_weights_pair<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      kernel_hwio, (__nv_bfloat16*)((unsigned char*)packed + c1::PACKED_ONE));
+  SHDR_LAUNCH_CHECK("k_pack_weights_pair");
   return SHDR_OK;
 }
 
@@ -437,8 +543,19 @@ extern "C" int shdr_frontend_conv1_f32(const float* img, const void* packed, con
   const long long nt = (long long)n * p.tiles_y * p.tiles_x;
   SHDR_REQUIRE(nt < 0x7fffffffLL && (long long)n * h * w < 0x7fffffffLL, "frontend_conv1: too many pixels for int32 tile indices");
   p.ntiles = (int)nt;
+  const int sms = sm_count(g.dev);
+  if (nt >= 4) {
+    // CTA pairs (the two SMs of a TPC share every MMA and each half of the weights): clusters of 2, an even grid
+    p.wpk += c1::PACKED_ONE;
+    SHDR_CUDA(cudaFuncSetAttribute(c1::k_frontend_conv1_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, c1::SMEM_BYTES));
+    const long long pairs = (nt + 1) / 2;
+    const int grid = 2 * (int)(pairs < sms / 2 ? pairs : sms / 2);
+    c1::k_frontend_conv1_pair<<<grid, c1::NTHREADS, c1::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    SHDR_LAUNCH_CHECK("k_frontend_conv1_pair");
+    return SHDR_OK;
+  }
   SHDR_CUDA(cudaFuncSetAttribute(c1::k_frontend_conv1, cudaFuncAttributeMaxDynamicSharedMemorySize, c1::SMEM_BYTES));
-  const int grid = (int)(nt < sm_count(g.dev) ? nt : sm_count(g.dev));
+  const int grid = (int)(nt < sms ? nt : sms);
   c1::k_frontend_conv1<<<grid, c1::NTHREADS, c1::SMEM_BYTES, (cudaStream_t)stream>>>(p);
   SHDR_LAUNCH_CHECK("k_frontend_conv1");
   return SHDR_OK;
