@@ -22,12 +22,21 @@
 // K is split into three passes of 32 channels (channels 0-31 | 32-63 | 64-92 + 3 zeros) that alternate between two
 // 51 KB feature buffers, so that the CUDA cores generate one pass while the tensor cores consume the other.
 //
-// Roles of the persistent CTA (one per SM, 15 warps): 8 producer warps (one thread per input pixel of the 37 x 21
+// Roles of the persistent CTA (one per SM, 16 warps): 9 producer warps (one thread per input pixel of the 37 x 21
 // halo tile: Sobel / votes of the pass, bf16 pack, four 16-byte shared stores), 1 thread streaming the packed weights
 // (one kernel row of one pass = 28 KB per 1-D bulk copy into a 4-stage ring), 2 warps issuing the MMAs (alternating
 // kernel rows, one elected lane, 14 MMAs per row back to back, 294 per tile),
 // 4 epilogue warps (tcgen05.ld of the two partial accumulators, add, scale / shift / ReLU, 256 B per output pixel to
 // HBM; two tiles' accumulators in tensor memory, so the epilogue of one tile overlaps the MMAs of the next).
+//
+// CTA pairs (the default; k_frontend_conv1_pair, clusters of 2 = the two SMs of a TPC).  Every MMA is issued with
+// cta_group::2 by the even CTA: M = 256 = this CTA's tile and the peer's, each CTA reads its own A and only HALF of B
+// (32 of the 64 output channels) from its own shared memory, and each accumulates its 128 rows in its own tensor
+// memory.  Per SM that is 5 KB instead of 6 KB of operand reads per MMA and half the weight bytes written into shared
+// memory and read from L2.  The peer has no issuer: its producers and epilogue report to the leader's barriers with
+// remote arrives, one of its idle threads relays "my half of ring stage s has landed", and the leader's commits are
+// multicast to the barriers of both CTAs.  A pair whose second tile index falls off the end runs a dummy tile there.
+// Inputs with fewer than 4 tiles take the single-CTA kernel (same code, PAIR = false).
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -63,9 +72,9 @@ template <bool PAIR> struct Ring {
   static constexpr int KSTEP = TAP / 2;                   // bytes of one 16-channel step of a tap
   static constexpr int LBO = KSTEP / 2;                   // K half
 };
-constexpr int NPROD = 256;                // producer threads (warps 0..7)
-constexpr int W_LOAD = 8, W_MMA = 9;      // warps 9, 10: MMA issuers; warps 11..14: epilogue
-constexpr int NTHREADS = 15 * 32;
+constexpr int NPROD = 288;                // producer threads (warps 0..8): 777 halo pixels = 2.7 per thread
+constexpr int W_LOAD = 9, W_MMA = 10;     // warps 10, 11: MMA issuers; warps 12..15: epilogue
+constexpr int NTHREADS = 16 * 32;
 constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer warps x (128 x 64 fp32)
 constexpr size_t PACKED_ONE = (size_t)NPASS * NTAP * WTAP;     // 602112: one operand image of the whole kernel
 constexpr size_t PACKED_BYTES = 2 * PACKED_ONE;                // the single-CTA image, then the CTA-pair image
