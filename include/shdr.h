@@ -103,8 +103,10 @@ int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h, int w, vo
  * against the same convolution of bf16-rounded features and weights it is fp32 summation-order noise.
  *
  * shdr_conv1_pack_weights_f32: kernel_hwio is conv1's variable [7][7][93][64] (device, fp32, the layout Keras
- * stores); packed receives shdr_conv1_packed_bytes() bytes: bf16, K split into (img, edges, hist4, hist8 | hist16),
- * each tap an operand image the tensor cores read as is.  Re-pack whenever the weights change.
+ * stores); packed receives shdr_conv1_packed_bytes() bytes: bf16, K in three passes of 32 channels, every tap an
+ * operand image the tensor cores read as is -- once for the single-CTA kernel and once split by output-channel half
+ * for the CTA-pair kernel (cta_group::2), which is used whenever the input has at least 4 output tiles of 16 x 8.
+ * Re-pack whenever the weights change.
  * shdr_frontend_conv1_f32: img [n,h,w,3] -> out [n, ceil(h/2), ceil(w/2), 64] fp32 =
  *   act((conv) * scale[o] + shift[o]);  scale NULL = 1, shift NULL = 0 (shift = the conv bias for a plain
  *   conv1; a folded batch norm gives both), relu != 0 applies max(., 0).  h, w >= 2. */

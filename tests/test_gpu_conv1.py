@@ -98,6 +98,16 @@ def test_frontend_conv1_many_tiles_and_repeat(shdr_gpu):
     assert np.abs(a - ref).max() <= TOL_EXACT * np.abs(ref).max()
 
 
+def test_frontend_conv1_pair_odd_tile_count(shdr_gpu):
+    """CTA-pair kernel with an ODD number of tiles spread over several iterations: the last pair runs a dummy tile in
+    its second CTA (481 tiles = 13 x 37 on 74 clusters), and partial tiles on the right and bottom edges."""
+    img, kern, bias = _case((1, 400, 584, 3), 31)
+    got = _run(shdr_gpu, img, kern, bias)
+    ref = oracle.frontend_conv1(img, kern, bias, bf16_operands=True)
+    assert got.shape == ref.shape == (1, 200, 292, 64)
+    assert np.abs(got - ref).max() <= TOL_EXACT * np.abs(ref).max()
+
+
 def test_frontend_conv1_rejects_bad_arguments(shdr_gpu):
     D = shdr_gpu.DeviceArray.from_numpy
     with pytest.raises(ValueError):
