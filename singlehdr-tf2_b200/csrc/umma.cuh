@@ -16,9 +16,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // that are adjacent in K, sbo = byte distance between core matrices adjacent in M (or N).
 //   bits 0-13 start address >> 4 | 16-29 lbo >> 4 | 32-45 sbo >> 4 | 46-47 version (1 on sm_100) | 61-63 swizzle (0)
 __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-#ifdef SHDR_UMMA_SWAP   // development switch: the other reading of the two offsets (tools/microbench/umma_nosw.cu decides)
-  const uint32_t t = lbo_bytes; lbo_bytes = sbo_bytes; sbo_bytes = t;
-#endif
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
