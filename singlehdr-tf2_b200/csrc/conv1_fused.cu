@@ -22,11 +22,11 @@
 // K is split into three passes of 32 channels (channels 0-31 | 32-63 | 64-92 + 3 zeros) that alternate between two
 // 51 KB feature buffers, so that the CUDA cores generate one pass while the tensor cores consume the other.
 //
-// Roles of the persistent CTA (one per SM, 16 warps): 9 producer warps (one thread per input pixel of the 37 x 21
+// Roles of the persistent CTA (one per SM, 20 warps): 13 producer warps (one thread per input pixel of the 37 x 21
 // halo tile: Sobel / votes of the pass, bf16 pack, four 16-byte shared stores), 1 thread streaming the packed weights
 // (one kernel row of one pass = 28 KB per 1-D bulk copy into a 4-stage ring), 2 warps issuing the MMAs (alternating
 // kernel rows, one elected lane, 14 MMAs per row back to back, 294 per tile),
-// 4 epilogue warps (tcgen05.ld of the two partial accumulators, add, scale / shift / ReLU, 256 B per output pixel to
+// 4 epilogue warps (tcgen05.ld of the two partial accumulators, 16 columns at a time, add, scale / shift / ReLU, 256 B per output pixel to
 // HBM; two tiles' accumulators in tensor memory, so the epilogue of one tile overlaps the MMAs of the next).
 //
 // CTA pairs (the default; k_frontend_conv1_pair, clusters of 2 = the two SMs of a TPC).  Every MMA is issued with
@@ -72,9 +72,9 @@ template <bool PAIR> struct Ring {
   static constexpr int KSTEP = TAP / 2;                   // bytes of one 16-channel step of a tap
   static constexpr int LBO = KSTEP / 2;                   // K half
 };
-constexpr int NPROD = 288;                // producer threads (warps 0..8): 777 halo pixels = 2.7 per thread
-constexpr int W_LOAD = 9, W_MMA = 10;     // warps 10, 11: MMA issuers; warps 12..15: epilogue
-constexpr int NTHREADS = 16 * 32;
+constexpr int NPROD = 416;                // producer threads (warps 0..12): 777 halo pixels = 2 per thread (1.87)
+constexpr int W_LOAD = 13, W_MMA = 14;    // warps 14, 15: MMA issuers; warps 16..19: epilogue
+constexpr int NTHREADS = 20 * 32;
 constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer warps x (128 x 64 fp32)
 constexpr size_t PACKED_ONE = (size_t)NPASS * NTAP * WTAP;     // 602112: one operand image of the whole kernel
 constexpr size_t PACKED_BYTES = 2 * PACKED_ONE;                // the single-CTA image, then the CTA-pair image
@@ -420,21 +420,21 @@ __device__ void epilogue(const Params& p, uint64_t* afull, uint64_t* aempty, uin
     const bool ok = valid && oy < p.oh && ox < p.ow;
     float* o = p.out + (((size_t)k.n * p.oh + oy) * p.ow + ox) * OC;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float v[32], v2[32];                                 // the two issuer warps' partial sums
-      tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (ab * 2) * OC + half * 32, v);
-      tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (ab * 2 + 1) * OC + half * 32, v2);
+    for (int part = 0; part < 4; ++part) {                 // 16 output channels at a time (register budget of 20 warps)
+      float v[16], v2[16];                                 // the two issuer warps' partial sums
+      tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (ab * 2) * OC + part * 16, v);
+      tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (ab * 2 + 1) * OC + part * 16, v2);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += v2[i];
-      if (half == 1) {                                     // every value of this accumulator is in registers
+      for (int i = 0; i < 16; ++i) v[i] += v2[i];
+      if (part == 3) {                                     // every value of this accumulator is in registers
         fence_before_sync();
         if (PAIR) mbar_arrive_cluster(aempty_leader + ab * 8);
         else mbar_arrive(aempty + ab);
       }
       if (ok) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int ch = half * 32 + g * 4;
+        for (int g = 0; g < 4; ++g) {
+          const int ch = part * 16 + g * 4;
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (p.scale) sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch));
           if (p.shift) sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch));

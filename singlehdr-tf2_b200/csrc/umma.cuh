@@ -89,6 +89,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same for 16 columns (half the registers)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- CTA pairs (cta_group::2): two CTAs of a cluster, on the two SMs of one TPC, execute ONE MMA of M = 256 ---------
 // Each CTA supplies its own 128 rows of A and HALF of the N rows of B from its own shared memory (same offsets in both
 // CTAs) and receives its 128 rows of D in its own tensor memory; the even-ranked CTA issues for both.
