@@ -79,10 +79,11 @@ constexpr int TMEM_COLS = 256;            // two tiles in flight x two issuer wa
 constexpr size_t PACKED_ONE = (size_t)NPASS * NTAP * WTAP;     // 602112: one operand image of the whole kernel
 constexpr size_t PACKED_BYTES = 2 * PACKED_ONE;                // the single-CTA image, then the CTA-pair image
 constexpr int RAW_R = LR + 2, RAW_C = LC + 2;  // raw fp32 image tile with the Sobel halo: 39 x 23 pixels
-constexpr int RAWC = 24;                  // raw tile, per row and colour: 12 even columns then 12 odd columns (23 used)
-constexpr int RAWP = 3 * RAWC + 3;        // 75 floats per row: 75 = 11 (mod 32) keeps consecutive rows off each other's banks
-constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 11712
-constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 227040 (both modes: Ring::DEPTH * Ring::ROW == NWS * WROW)
+constexpr int RAWC = 24;                  // raw tile, per row and colour: 12 odd columns then 12 even columns (23 used)
+constexpr int RAWP = 3 * RAWC + 15;       // 87 floats per row: consecutive producer lanes (11 even + 10 odd tile columns,
+                                          // then the next row, 87 = 23 (mod 32) words on) read consecutive banks
+constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 13584
+constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 228912 (both modes: Ring::DEPTH * Ring::ROW == NWS * WROW)
 
 struct Params {
   const float* img;
@@ -140,8 +141,8 @@ __device__ __forceinline__ float feature(int ch, const float* v, const float* so
 
 // one input pixel, the 32 channels of pass PASS -> four 16-byte groups of the feature tile.  `r` points at the pixel
 // in the raw tile (its 3 x 3 neighbourhood is there too, REFLECTed at the image border by the staging step).
-// raw tile word of column rx (0..22), colour 0, in its row: even columns first, then the odd ones
-__device__ __forceinline__ int raw_col(int rx) { return (rx & 1) * (RAWC / 2) + (rx >> 1); }
+// raw tile word of column rx (0..22), colour 0, in its row: odd raw columns (= even tile columns) first, then the even ones
+__device__ __forceinline__ int raw_col(int rx) { return ((rx & 1) ^ 1) * (RAWC / 2) + (rx >> 1); }
 
 template <int PASS>
 __device__ __forceinline__ void gen_pixel(const float* __restrict__ row, int rx, unsigned char* dst) {
