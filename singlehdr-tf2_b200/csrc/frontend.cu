@@ -22,11 +22,13 @@ namespace shdr {
 constexpr int STRIP = 128;   // pixels (= threads) per CTA
 
 // HMASK: bit0 -> B=4, bit1 -> B=8, bit2 -> B=16.  FULL adds img(3)+edge(6) in front.
-template <bool FULL, int HMASK>
+// EDGES: the six Sobel channels alone (stand-alone tf.image.sobel_edges + reshape); needs FULL and HMASK == 0.
+template <bool FULL, int HMASK, bool EDGES = false>
 struct StripLayout {
-  static constexpr int HB = FULL ? 9 : 0;
+  static constexpr int HB = EDGES ? 6 : (FULL ? 9 : 0);
   static constexpr int CH = HB + ((HMASK & 1) ? 12 : 0) + ((HMASK & 2) ? 24 : 0) + ((HMASK & 4) ? 48 : 0);
-  static constexpr int CHP = (CH & 1) ? CH : CH + 1;   // odd per-pixel stride in shared memory
+  // odd per-pixel stride in shared memory (EDGES: 6, a 2-way conflict on six stores, so that the strip leaves as 128-bit words)
+  static constexpr int CHP = ((CH & 1) || EDGES) ? CH : CH + 1;
 };
 
 template <int B>
@@ -41,10 +43,10 @@ __device__ __forceinline__ void hist_bins_pow2(float v, float* o /* stride 3 bet
 // BF16: the strip is rounded to bfloat16 (round to nearest even) while it is streamed out -- the reduced-precision
 // output flag of SURVEY.md 8(f) rank 2 (halves the 372 B/px write that dominates this kernel's roofline time; changes
 // numerics, so it is a separate entry point and never the parity-gated default).
-template <bool FULL, int HMASK, bool BF16 = false>
+template <bool FULL, int HMASK, bool BF16 = false, bool EDGES = false>
 __global__ void __launch_bounds__(STRIP)
 k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx, int h, int w, int vec_ok) {
-  using L = StripLayout<FULL, HMASK>;
+  using L = StripLayout<FULL, HMASK, EDGES>;
   constexpr int CH = L::CH, CHP = L::CHP;
   __shared__ __align__(16) float s[STRIP * CHP];
   const int tid = threadIdx.x;
@@ -86,9 +88,9 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
         dx = __fadd_rn(dx, 2.0f * p12);
         dx = __fsub_rn(dx, p20);
         dx = __fadd_rn(dx, p22);
-        o[c] = v[c];
-        o[3 + c * 2 + 0] = dy;
-        o[3 + c * 2 + 1] = dx;
+        if (!EDGES) o[c] = v[c];
+        o[(EDGES ? 0 : 3) + c * 2 + 0] = dy;
+        o[(EDGES ? 0 : 3) + c * 2 + 1] = dx;
       }
     }
 #pragma unroll
@@ -144,10 +146,10 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
   }
 }
 
-template <bool FULL, int HMASK, bool BF16 = false>
+template <bool FULL, int HMASK, bool BF16 = false, bool EDGES = false>
 static int launch_strip(const float* img, float* out, long long npx, int h, int w, cudaStream_t st) {
   const unsigned grid = (unsigned)((npx + STRIP - 1) / STRIP);
-  k_frontend_strip<FULL, HMASK, BF16><<<grid, STRIP, 0, st>>>(img, out, (int)npx, h, w, aligned16(out) ? 1 : 0);
+  k_frontend_strip<FULL, HMASK, BF16, EDGES><<<grid, STRIP, 0, st>>>(img, out, (int)npx, h, w, aligned16(out) ? 1 : 0);
   SHDR_LAUNCH_CHECK("k_frontend_strip");
   return SHDR_OK;
 }
@@ -279,6 +281,9 @@ extern "C" int shdr_sobel6_f32(const float* img, float* out, int n, int h, int w
                "sobel6: out_ch_stride=%d out_ch_off=%d cannot hold %d channels", out_ch_stride, out_ch_off, 2 * c);
   DeviceGuard g(out);
   if (g.status != SHDR_OK) return g.status;
+  // the stand-alone RGB tensor takes the strip kernel (edges staged in shared memory, flat 128-bit stores)
+  if (c == 3 && out_ch_off == 0 && out_ch_stride == 6)
+    return launch_strip<true, 0, false, true>(img, out, (long long)n * h * w, h, w, (cudaStream_t)stream);
   return launch_sobel_generic(img, out, (long long)n * h * w, h, w, c, out_ch_stride, out_ch_off,
                               (cudaStream_t)stream, g.dev);
 }
