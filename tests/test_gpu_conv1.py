@@ -38,7 +38,8 @@ def _run(shdr, img, kern, bias=None, scale=None, relu=False):
 
 
 @pytest.mark.parametrize("shape", [(1, 32, 16, 3), (2, 64, 48, 3), (1, 33, 17, 3), (3, 2, 2, 3), (1, 7, 100, 3),
-                                   (1, 70, 6, 3), (2, 45, 51, 3)])
+                                   (1, 70, 6, 3), (2, 45, 51, 3), (2, 101, 77, 3), (1, 64, 258, 3), (5, 18, 34, 3),
+                                   (1, 3, 3, 3), (1, 31, 130, 3)])
 def test_frontend_conv1_matches_oracle(shdr_gpu, shape):
     img, kern, bias = _case(shape, sum(shape))
     got = _run(shdr_gpu, img, kern, bias)
