@@ -16,7 +16,7 @@ from .layers import (                                                      # noq
     AEInvcrfDecodeNet, model,
 )
 from .host import (                                                        # noqa: F401
-    HostPipeline, frontend_host, hist_multi_host, linearize_host, apply_rf_host,
+    HostPipeline, frontend_host, frontend_conv1_host, hist_multi_host, linearize_host, apply_rf_host,
 )
 from .sharding import shard_range, row_tiles                              # noqa: F401
 

@@ -104,6 +104,56 @@ def frontend_host(img, out=None, pool=False, device=0):
     return out
 
 
+def frontend_conv1_host(img, kernel, bias=None, scale=None, relu=False, out=None, device=0):
+    """numpy ``[n,h,w,3]`` + conv1's kernel ``[7,7,93,64]`` (and bias / folded-norm scale ``[64]``) -> numpy
+    ``[n, ceil(h/2), ceil(w/2), 64]``: the front end fused into ``crfFeatureNet.conv1`` (tensor cores, bf16 operands).
+    Per input pixel 12 B go to the device and 64 B come back -- against 372 B for the 93-channel tensor."""
+    img = _as_f32(img)
+    n, h, w, c = img.shape
+    if c != 3:
+        raise ValueError("frontend_conv1: img must have 3 channels")
+    kernel = _as_f32(kernel)
+    if kernel.shape != (7, 7, N.FRONTEND_CH, 64):
+        raise ValueError(f"frontend_conv1: kernel must be [7,7,93,64], got {kernel.shape}")
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    if out is None:
+        out = np.empty((n, oh, ow, 64), np.float32)
+    N.require_gpu()
+    small = {"kernel": kernel}
+    for name, v in (("bias", bias), ("scale", scale)):
+        if v is not None:
+            v = _as_f32(v)
+            if v.shape != (64,):
+                raise ValueError(f"frontend_conv1: {name} must be [64], got {v.shape}")
+            small[name] = v
+    dev = {k: C.c_void_p() for k in list(small) + ["packed"]}
+    try:
+        for k, v in small.items():
+            N.check(N.lib.shdr_malloc(C.byref(dev[k]), v.nbytes, device))
+            N.check(N.lib.shdr_h2d(dev[k].value, v.ctypes.data, v.nbytes, device, None))
+        N.check(N.lib.shdr_malloc(C.byref(dev["packed"]), int(N.lib.shdr_conv1_packed_bytes()), device))
+        N.check(N.lib.shdr_conv1_pack_weights_f32(dev["kernel"].value, dev["packed"].value, None))
+        N.check(N.lib.shdr_sync(device))
+        d_scale = dev["scale"].value if "scale" in dev else None
+        d_bias = dev["bias"].value if "bias" in dev else None
+
+        def op(d_in, d_out, m, st, _i0):
+            N.check(N.lib.shdr_frontend_conv1_f32(d_in, dev["packed"].value, d_scale, d_bias, 1 if relu else 0, d_out,
+                                                  m, h, w, st))
+
+        ib, ob = h * w * 3 * 4, oh * ow * 64 * 4
+        p = HostPipeline(op, ib, ob, _chunk_for(ob, n, 64 << 20), device)
+        try:
+            p.run(img, out, n)
+        finally:
+            p.close()
+    finally:
+        for v in dev.values():
+            if v.value:
+                N.lib.shdr_free(v.value, device)
+    return out
+
+
 def hist_multi_host(img, out=None, pool=False, device=0):
     """numpy ``[n,h,w,3]`` -> numpy ``[n,h,w,84]`` (hist4 | hist8 | hist16, optionally pooled)."""
     img = _as_f32(img)

@@ -109,6 +109,17 @@ def test_frontend_conv1_pair_odd_tile_count(shdr_gpu):
     assert np.abs(got - ref).max() <= TOL_EXACT * np.abs(ref).max()
 
 
+def test_frontend_conv1_host_pipeline(shdr_gpu):
+    """numpy in / numpy out through the pipelined host API (several chunks), with scale + bias + ReLU."""
+    img, kern, bias = _case((5, 96, 80, 3), 41)
+    scale = np.random.default_rng(42).uniform(0.5, 2.0, 64).astype(np.float32)
+    got = shdr_gpu.frontend_conv1_host(img, kern, bias=bias, scale=scale, relu=True)
+    conv = oracle.frontend_conv1(img, kern, None, bf16_operands=True)
+    ref = np.maximum(conv * scale + bias, 0.0)
+    assert got.shape == (5, 48, 40, 64)
+    assert np.abs(got - ref).max() <= TOL_EXACT * np.abs(conv).max() * 2.0
+
+
 def test_frontend_conv1_rejects_bad_arguments(shdr_gpu):
     D = shdr_gpu.DeviceArray.from_numpy
     with pytest.raises(ValueError):
