@@ -93,6 +93,14 @@ def test_argument_validation_messages():
     g = np.zeros(10, np.float32)
     rc = N.lib.shdr_set_emor_table(g.ctypes.data, g.ctypes.data, 10, 11)
     assert rc == N.ERR_INVALID
+    # the fused conv1 entry points (two bf16 operand images of the 7x7x96x64 kernel: single CTA and CTA pair)
+    assert N.lib.shdr_conv1_packed_bytes() == 2 * 49 * 96 * 64 * 2
+    rc = N.lib.shdr_frontend_conv1_f32(None, None, None, None, 0, None, 1, 8, 8, None)
+    assert rc == N.ERR_INVALID and "NULL" in N.last_error()
+    rc = N.lib.shdr_frontend_conv1_f32(None, None, None, None, 0, None, 0, 8, 8, None)   # empty batch is a no-op
+    assert rc == N.OK
+    rc = N.lib.shdr_conv1_pack_weights_f32(None, None, None)
+    assert rc == N.ERR_INVALID
 
 
 def test_dlpack_rejects_cpu_tensors():
