@@ -506,6 +506,8 @@ __device__ __forceinline__ void conv1_body(const Params& p) {
   }
 }
 
+#undef SHDR_FOR_TILES
+
 __global__ void __launch_bounds__(NTHREADS, 1) k_frontend_conv1(const Params p) { conv1_body<false>(p); }
 // CTA pairs: the two CTAs of a cluster sit on the two SMs of one TPC and share every MMA (cta_group::2)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_frontend_conv1_pair(const Params p) {
