@@ -40,8 +40,18 @@
 
 #include "common.cuh"
 
+// This file is compiled twice: as is (rows leave as bulk copies: the hot path) and, through pooled_slide_nb.cu, with
+// SHDR_SLIDE_NOBULK (rows leave as cooperative 4-byte stores: 93 channels with w % 4 != 0, or an unaligned output).
+// Two translation units, because merely instantiating a second variant next to the hot kernel changed ptxas' code for
+// it (measured: 0.621 instead of 0.597 ms on config2).
+#ifndef SHDR_SLIDE_NOBULK
+#define SHDR_SL_NS sl
+#else
+#define SHDR_SL_NS sl_nb
+#endif
+
 namespace shdr {
-namespace sl {
+namespace SHDR_SL_NS {
 
 constexpr int PK = 16, HL = 7, HR = 8;       // TF SAME: 7 before, 8 after
 constexpr int SW = 64;                       // output columns per strip
@@ -425,6 +435,7 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
         o[3 + fc * 2] = fdy;
         o[4 + fc * 2] = fdx;
       }
+#ifndef SHDR_SLIDE_NOBULK
       fence_async_smem();                  // staging writes -> visible to the bulk-copy (async) proxy
       if (elected) bulk_wait_read();       // the previous row's store has left the OTHER staging buffer
       named_bar_sync(1 + g, GROUP);        // the whole row is staged; the other buffer is free for the next row
@@ -432,9 +443,19 @@ __device__ __forceinline__ void consumer(const Params& p, const int* __restrict_
         bulk_store(orow, stg, (unsigned)(vw * CO * 4));
         bulk_commit();
       }
+#else
+      // rows that are not 16-byte aligned chunks: the group streams the staged row out with coalesced 4-byte stores;
+      // every thread is past this loop before it reaches the next row's barrier, i.e. before anybody writes this
+      // staging buffer again (two rows on)
+      named_bar_sync(1 + g, GROUP);
+      const int nfl = vw * CO;
+      for (int i = gtid; i < nfl; i += GROUP) st_stream1(orow + i, stg[i]);
+#endif
     }
   }
+#ifndef SHDR_SLIDE_NOBULK
   if (elected) bulk_wait_all();
+#endif
 }
 
 template <bool FULL>
@@ -474,16 +495,21 @@ static int launch_t(const Params& p, int sms, cudaStream_t st) {
   return SHDR_OK;
 }
 
-}  // namespace sl
+}  // namespace sl / sl_nb
+
+#ifdef SHDR_SLIDE_NOBULK
+int launch_pool_slide_nobulk(const sl_nb::Params& p0, bool full93, int sms, cudaStream_t st) {
+  return full93 ? sl_nb::launch_t<true>(p0, sms, st) : sl_nb::launch_t<false>(p0, sms, st);
+}
+#else
+namespace sl_nb { struct Params; }
+int launch_pool_slide_nobulk(const sl_nb::Params& p0, bool full93, int sms, cudaStream_t st);   // pooled_slide_nb.cu
 
 // true when the sliding-window kernel can run this request: the {4, 8, 16} histograms into a dense 84-channel tensor,
 // or (full93) into channels 9..92 of the 93-channel front-end tensor together with img + Sobel in channels 0..8.
-// The per-row bulk copies need 16-byte aligned chunks: always true for 84 channels (336 B per pixel); for 93 channels
-// (372 B per pixel) the image width must be a multiple of 4.
 bool pool_slide_supported(const float* out, int w, const int* bins, int nbins, bool full93) {
-  if (nbins != 3 || bins[0] != 4 || bins[1] != 8 || bins[2] != 16) return false;
-  if (!aligned16(out)) return false;
-  return full93 ? (w % 4) == 0 : true;
+  (void)out; (void)w; (void)full93;
+  return nbins == 3 && bins[0] == 4 && bins[1] == 8 && bins[2] == 16;
 }
 
 int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool full93, int dev, cudaStream_t st) {
@@ -509,7 +535,14 @@ int launch_pool_slide(const float* img, float* out, int n, int h, int w, bool fu
   SHDR_REQUIRE(total > 0 && total < 0x7fffffffLL, "pool_slide: %lld tasks out of range", total);
   SHDR_REQUIRE((long long)h * w * 3 < 0x7fffffffLL, "pool_slide: one image of %d x %d exceeds the 32-bit row offsets", h, w);
   p.ntasks = (int)total;
+  // The per-row bulk copies need 16-byte aligned chunks: always true for 84 channels (336 B per pixel); for 93 channels
+  // (372 B per pixel) the image width must be a multiple of 4.  Otherwise: the same kernel with cooperative row stores
+  // (identical Params layout, its own translation unit).
+  if (!aligned16(out) || (full93 && (w % 4) != 0))
+    return launch_pool_slide_nobulk(reinterpret_cast<const sl_nb::Params&>(p), full93, sms, st);
   return full93 ? sl::launch_t<true>(p, sms, st) : sl::launch_t<false>(p, sms, st);
 }
+
+#endif  // SHDR_SLIDE_NOBULK
 
 }  // namespace shdr

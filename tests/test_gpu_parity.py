@@ -208,6 +208,19 @@ def test_frontend_pooled(shdr_gpu, golden_small):
     assert_rel(got[..., 9:], ref[..., 9:], RTOL_POOL)
 
 
+@pytest.mark.parametrize("shape", [(2, 40, 70, 3), (1, 33, 131, 3), (1, 70, 65, 3)])
+def test_frontend_pooled_width_not_multiple_of_4(shdr_gpu, shape):
+    """93 channels x a width that is not a multiple of 4: output rows are not 16-byte aligned chunks, so the
+    sliding-window kernel writes them with cooperative 4-byte stores instead of bulk copies (same kernel, same values)."""
+    img = rnd(shape, sum(shape))
+    before = shdr_gpu.launch_count()
+    got = shdr_gpu.frontend(shdr_gpu.DeviceArray.from_numpy(img), pool=True).numpy()
+    assert shdr_gpu.launch_count() - before == 1           # ONE launch, not copy + Sobel + generic pooled
+    ref = oracle.frontend(img, pool_k=16)
+    assert np.array_equal(got[..., :9], ref[..., :9])
+    assert_rel(got[..., 9:], ref[..., 9:], RTOL_POOL)
+
+
 # ---------------------------------------------------------------- inverse CRF
 def test_invcrf_build_and_increase(shdr_gpu, emor):
     _, g0, hinv = emor
