@@ -406,6 +406,35 @@ def conv1_e2e(torch, dist, N, keep, nb, h, w, dev, steps=3):
     return out
 
 
+def conv1_library_route(torch, N, keep, nb, h, w, dev, sh, steps=10):
+    """The same result by the library route, for comparison only: this repo's bf16 front end writes the 93-channel
+    tensor to HBM, then cuDNN's bf16 convolution (through torch, channels-last) reads it back."""
+    try:
+        img, kern, bias = keep[0], keep[5], keep[6]
+        feat = torch.empty((nb, h, w, 93), device=dev, dtype=torch.bfloat16)
+        wt = kern.permute(3, 2, 0, 1).contiguous(memory_format=torch.channels_last).bfloat16()
+        bb = bias.bfloat16()
+        ph, pw = max((((h + 1) // 2) - 1) * 2 + 7 - h, 0), max((((w + 1) // 2) - 1) * 2 + 7 - w, 0)
+
+        def route():
+            N.check(N.lib.shdr_frontend_bf16(img.data_ptr(), feat.data_ptr(), nb, h, w, sh))
+            x = torch.nn.functional.pad(feat.permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+            return torch.nn.functional.conv2d(x, wt, bb, stride=2)
+        for _ in range(3):
+            route()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            route()
+        e1.record()
+        torch.cuda.synchronize()
+        return {"ms_per_step": e0.elapsed_time(e1) / steps,
+                "what": "shdr_frontend_bf16 -> HBM -> torch.nn.functional.conv2d (cuDNN, bf16, channels-last), this rank"}
+    except Exception as e:                      # no cuDNN / out of memory: the comparison is optional
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def sub_record(torch, dist, N, stream, dev, rank, world, wl, nb, steps, warmup, scaling):
     """One extra workload measured with the same rules, reported inside the main JSON line."""
     _, h, w, bpp, desc = WORKLOADS[wl]
@@ -417,6 +446,7 @@ def sub_record(torch, dist, N, stream, dev, rank, world, wl, nb, steps, warmup, 
     ms_step, kern_ms = timed_region(torch, dist, stream, dev, step, steps, warmup, flush)
     peak, _ = load_peak()
     e2e_c = conv1_e2e(torch, dist, N, keep, nb, h, w, dev) if wl == "config4c" else None
+    lib_c = conv1_library_route(torch, N, keep, nb, h, w, dev, stream.cuda_stream) if wl == "config4c" else None
     del keep
     torch.cuda.empty_cache()
     rec = {"metric": "Mpixel/s", "value": world * px / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world,
@@ -433,6 +463,7 @@ def sub_record(torch, dist, N, stream, dev, rank, world, wl, nb, steps, warmup, 
         rec["hbm_roofline_frac"] = rec.pop("roofline_frac")
         rec["input_mpixel_per_s"] = rec["value"]
         rec["e2e"] = e2e_c
+        rec["library_route"] = lib_c
     return rec
 
 
