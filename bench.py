@@ -457,6 +457,8 @@ def sub_record(torch, dist, N, stream, dev, rank, world, wl, nb, steps, warmup, 
         tfl = nb * ((h + 1) // 2) * ((w + 1) // 2) * CONV1_FLOP_PER_OUT_PX / (kern_ms * 1e-3) / 1e12
         rec["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
                            "peak_source": tsrc, "dtype": "bf16 operands, f32 accumulate",
+                           "traffic": load_traffic("config4c"),
+                           "algorithmic_bytes_per_launch": px * bpp,
                            "note": "N = 64 output channels: per 128x64x16 MMA (32 clocks of math) an SM reads 5 KB of shared-memory "
                                    "operands in CTA-pair mode (6 KB alone), so the 128 B/clk shared-memory port caps this "
                                    "shape at 0.8 of the tensor peak"}

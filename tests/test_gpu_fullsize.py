@@ -118,3 +118,28 @@ def test_config4p_pooled_frontend_full(shdr_gpu):
     assert np.array_equal(f[..., :9], ref[..., :9])
     assert np.all(np.abs(f[..., 9:] - ref[..., 9:]) <= 1e-5 * np.abs(ref[..., 9:]))
     assert np.array_equal(f[..., 9:], shdr_gpu.hist_multi(d, pool=True).numpy())
+
+
+def test_config4_frontend_conv1_full(shdr_gpu):
+    """configs[3] shape, 8 x 512 x 512, through the fused front end + conv1 kernel (4096 tiles, 28 iterations of
+    every CTA pair).  The convolution is local (an output pixel sees the input within +-6 pixels), so the oracle is
+    run on crops: the interior of a crop's result must equal the full-size result, and crops touching the image
+    corners check the 'SAME' padding and the REFLECT Sobel at the border."""
+    rng = np.random.default_rng(44)
+    img = rng.random((8, 512, 512, 3), dtype=np.float32)
+    kern = (rng.normal(0, 1, (7, 7, 93, 64)) / 67.5).astype(np.float32)
+    bias = rng.normal(0, 0.1, 64).astype(np.float32)
+    D = shdr_gpu.DeviceArray.from_numpy
+    out = shdr_gpu.frontend_conv1(D(img), shdr_gpu.conv1_pack_weights(D(kern)), bias=D(bias)).numpy()
+    assert out.shape == (8, 256, 256, 64) and np.isfinite(out).all()
+    scale = np.abs(out).max()
+    M = 8                                             # even margin (input pixels) dropped around an interior crop
+    boxes = [(0, 0, 0), (3, 0, 416), (5, 416, 0), (7, 416, 416)]                     # (image, y0, x0): the four corners
+    boxes += [(int(rng.integers(0, 8)), int(rng.integers(8, 200)) * 2, int(rng.integers(8, 200)) * 2) for _ in range(6)]
+    for n, y0, x0 in boxes:
+        crop = img[n:n + 1, y0:y0 + 96, x0:x0 + 96]
+        ref = oracle.frontend_conv1(crop, kern, bias, bf16_operands=True)          # [1, 48, 48, 64]
+        ya, yb = (0 if y0 == 0 else M // 2), (48 if y0 + 96 == 512 else 48 - M // 2)
+        xa, xb = (0 if x0 == 0 else M // 2), (48 if x0 + 96 == 512 else 48 - M // 2)
+        got = out[n, y0 // 2 + ya:y0 // 2 + yb, x0 // 2 + xa:x0 // 2 + xb]
+        assert np.abs(got - ref[0, ya:yb, xa:xb]).max() <= 2e-5 * scale, (n, y0, x0)
