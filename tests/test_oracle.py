@@ -215,3 +215,39 @@ def test_golden_regression(golden_small, emor):
     np.testing.assert_allclose(oracle.invcrf_pca_w_2_invcrf(g["w"], g0, hinv), g["pca"], atol=1e-6)
     np.testing.assert_allclose(oracle.increase(g["pca"]), g["curve"], atol=2e-6)
     np.testing.assert_allclose(oracle.apply_rf(g["x"], g["curve"]), g["lin"], atol=1e-6)
+
+
+# ---------------------------------------------------------------- conv1 restatement
+@pytest.mark.parametrize("h,w", [(12, 16), (13, 9), (7, 7), (2, 2), (31, 18)])
+def test_conv_same_s2_vs_torch(h, w):
+    """tf.keras.layers.Conv2D(64, (7,7), strides 2, 'SAME') semantics (linearization_net.py:91): out = ceil(in/2), pad
+    = max((out-1)*2 + 7 - in, 0) with the smaller half in front, cross-correlation -- against stock CPU PyTorch with
+    the same explicit padding."""
+    rng = np.random.default_rng(h * 100 + w)
+    x, k, b = rng.normal(size=(2, h, w, 5)), rng.normal(size=(7, 7, 5, 4)), rng.normal(size=4)
+    got = oracle.conv2d_same_s2(x, k, b)
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    ph, pw = max((oh - 1) * 2 + 7 - h, 0), max((ow - 1) * 2 + 7 - w, 0)
+    xt = F.pad(torch.from_numpy(x).permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+    ref = F.conv2d(xt, torch.from_numpy(k).permute(3, 2, 0, 1), torch.from_numpy(b), stride=2).permute(0, 2, 3, 1).numpy()
+    assert got.shape == (2, oh, ow, 4)
+    assert np.abs(got - ref).max() < 1e-12
+
+
+def test_bf16_round_vs_torch():
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.normal(size=4096), rng.random(4096), [0.0, 1.0, 1.00390625, 1.01171875, -2.5e-3, 3.0e38]]).astype(np.float32)
+    assert np.array_equal(oracle.bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+def test_frontend_conv1_composition():
+    """frontend_conv1 == conv2d_same_s2(frontend(img)); the bf16-operand variant differs by the rounding only."""
+    rng = np.random.default_rng(1)
+    img = rng.random((1, 20, 14, 3), dtype=np.float32)
+    kern = (rng.normal(size=(7, 7, 93, 64)) / 67.5).astype(np.float32)
+    bias = rng.normal(0, 0.1, 64).astype(np.float32)
+    full = oracle.frontend_conv1(img, kern, bias)
+    assert np.array_equal(full, oracle.conv2d_same_s2(oracle.frontend(img), kern, bias))
+    b16 = oracle.frontend_conv1(img, kern, bias, bf16_operands=True)
+    assert full.shape == b16.shape == (1, 10, 7, 64)
+    assert 0 < np.abs(full - b16).max() < 1e-2 * np.abs(full).max()
