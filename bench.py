@@ -44,7 +44,7 @@ WORKLOADS = {
                  "93-channel front end with the 16x16 'same' pool fused (one launch), batch 8 x 512x512x3"),
     "config4c": (8, 512, 512, 76,
                  "configs[3] first stage: front end fused into crfFeatureNet.conv1 (7x7/2 'SAME', 93 -> 64, bias) on the "
-                 "tensor cores (bf16 operands, fp32 accumulate), batch 8 x 512x512x3 -> [8,256,256,64]; the 93-channel "
+                 "tensor cores (fp16 operands, fp32 accumulate), batch 8 x 512x512x3 -> [8,256,256,64]; the 93-channel "
                  "tensor never reaches HBM"),
     "config2u": (32, 512, 512, 348,
                  "soft histogram B={4,8,16} WITHOUT the pool (as the reference ships it), batch 32 x 512x512x3 -> 84 ch"),
@@ -75,7 +75,7 @@ def load_peak():
 
 
 def load_tensor_peak():
-    """bf16 dense tensor peak (TFLOP/s): the burst figure, for a kernel timed alone."""
+    """Dense 16-bit (bf16 = fp16 rate) tensor peak (TFLOP/s): the burst figure, for a kernel timed alone."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
@@ -452,11 +452,11 @@ def sub_record(torch, dist, N, stream, dev, rank, world, wl, nb, steps, warmup, 
     rec = {"metric": "Mpixel/s", "value": world * px / (ms_step * 1e-3) / 1e6, "unit": "Mpixel/s", "n_gpus": world,
            "steps": steps, "ms_per_step": ms_step, "scaling": scaling, "config": config_dict(wl, world, nb),
            "roofline_frac": px * bpp / (kern_ms * 1e-3) / 1e9 / peak}
-    if wl == "config4c":       # the one tensor-bound kernel: roofline against the measured bf16 GEMM peak
+    if wl == "config4c":       # the one tensor-bound kernel: roofline against the measured 16-bit GEMM peak
         tpeak, tsrc = load_tensor_peak()
         tfl = nb * ((h + 1) // 2) * ((w + 1) // 2) * CONV1_FLOP_PER_OUT_PX / (kern_ms * 1e-3) / 1e12
         rec["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
-                           "peak_source": tsrc, "dtype": "bf16 operands, f32 accumulate",
+                           "peak_source": tsrc, "dtype": "fp16 operands, f32 accumulate (peak: cuBLAS bf16 GEMM, the same tensor-core rate)",
                            "traffic": load_traffic("config4c"),
                            "algorithmic_bytes_per_launch": px * bpp,
                            "note": "N = 64 output channels: per 128x64x16 MMA (32 clocks of math) an SM reads 5 KB of shared-memory "

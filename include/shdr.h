@@ -96,14 +96,16 @@ int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h, int w, vo
  *        ->  crfFeatureNet.conv1 = Conv2D(64, (7,7), strides (2,2), padding 'SAME', bias)
  *            (linearization_net.py:91,107)
  * and optionally the inference-mode norm1 + act1 behind it (:108-109) as a per-channel scale / shift / ReLU.
- * The 93-channel tensor never reaches HBM: each CTA builds the bf16 feature tile of a 16 x 8 block of output
+ * The 93-channel tensor never reaches HBM: each CTA builds the fp16 feature tile of a 16 x 8 block of output
  * pixels in shared memory and contracts it with the 7x7x93x64 kernel on the tensor cores (tcgen05, fp32
- * accumulation).  bf16 operands change numerics, so this is a separate entry point and never the parity-gated
- * fp32 default: against the fp32 convolution of the fp32 features the error is ~3e-3 of the output's scale;
- * against the same convolution of bf16-rounded features and weights it is fp32 summation-order noise.
+ * accumulation).  Half-precision (IEEE fp16) operands change numerics, so this is a separate entry point and never the
+ * parity-gated fp32 default: against the fp32 convolution of the fp32 features the error is ~3e-4 of the output's
+ * scale (fp16 rather than bf16: every operand is O(1), and 11 instead of 8 significand bits come at the same
+ * tensor-core rate; values beyond +-65504 saturate); against the same convolution of fp16-rounded features and
+ * weights it is fp32 summation-order noise.
  *
  * shdr_conv1_pack_weights_f32: kernel_hwio is conv1's variable [7][7][93][64] (device, fp32, the layout Keras
- * stores); packed receives shdr_conv1_packed_bytes() bytes: bf16, K in three passes of 32 channels, every tap an
+ * stores); packed receives shdr_conv1_packed_bytes() bytes: fp16, K in three passes of 32 channels, every tap an
  * operand image the tensor cores read as is -- once for the single-CTA kernel and once split by output-channel half
  * for the CTA-pair kernel (cta_group::2), which is used whenever the input has at least 4 output tiles of 16 x 8.
  * Re-pack whenever the weights change.

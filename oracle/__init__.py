@@ -36,6 +36,6 @@ from .np_oracle import (  # noqa: F401
     parse_invemor, parse_table, invcrf_pca_w_2_invcrf, increase, apply_rf,
     linearize, hist_centers,
     clip01, alpha_mask, linearize_ex, synth_ldr,
-    bf16_round, conv2d_same_s2, frontend_conv1,
+    bf16_round, half_round, conv2d_same_s2, frontend_conv1,
     apply_rf_grad, increase_grad, invcrf_pca_grad, histogram_layer_grad, sobel_edges6_grad, frontend_grad,
 )

@@ -144,6 +144,13 @@ def bf16_round(x):
     return ((u + r) & 0xFFFF0000).astype(np.uint32).view(np.float32)
 
 
+def half_round(x):
+    """float32 -> IEEE half (round to nearest even, subnormals kept) -> float32, saturating at +-65504 instead of
+    overflowing to inf (what the fused conv1 kernel does to its operands); NaN stays NaN."""
+    x = np.asarray(x, dtype=np.float32)
+    return np.clip(x, np.float32(-65504.0), np.float32(65504.0)).astype(np.float16).astype(np.float32)
+
+
 def conv2d_same_s2(x, kernel, bias=None, dtype=np.float64):
     """``tf.keras.layers.Conv2D(filters, (kh, kw), strides=(2, 2), padding='SAME')`` on NHWC ``x`` with an HWIO
     ``kernel`` -- ``crfFeatureNet.conv1``, linearization_net.py:91,107 (7x7, 93 -> 64, bias).  TF 'SAME':
@@ -166,14 +173,14 @@ def conv2d_same_s2(x, kernel, bias=None, dtype=np.float64):
     return out
 
 
-def frontend_conv1(img, kernel, bias=None, bf16_operands=False, dtype=np.float64):
+def frontend_conv1(img, kernel, bias=None, half_operands=False, dtype=np.float64):
     """``crfFeatureNet.conv1(concat([img, edge6, hist4, hist8, hist16]))``: linearization_net.py:312-322 -> :107.
-    The features are the fp32 ones of :func:`frontend`; ``bf16_operands=True`` rounds features and kernel to bfloat16
+    The features are the fp32 ones of :func:`frontend`; ``half_operands=True`` rounds features and kernel to fp16
     first (what the fused tensor-core kernel multiplies), the sum is carried in ``dtype``."""
     feat = frontend(img)
     kernel = np.asarray(kernel, np.float32)
-    if bf16_operands:
-        feat, kernel = bf16_round(feat), bf16_round(kernel)
+    if half_operands:
+        feat, kernel = half_round(feat), half_round(kernel)
     return conv2d_same_s2(feat, kernel, bias, dtype)
 
 

@@ -4,18 +4,18 @@
 //   features = tf.concat([img, sobel6, hist4, hist8, hist16], -1)            linearization_net.py:312-322
 //   conv1    = Conv2D(64, (7,7), strides (2,2), padding 'SAME', bias)(features)   linearization_net.py:91,107
 // The 93-channel tensor (372 B per input pixel) is the front end's whole HBM cost and conv1 reduces it 4x
-// spatially right away.  Here it never exists in HBM: every CTA generates the bf16 feature tile of one 16 x 8
+// spatially right away.  Here it never exists in HBM: every CTA generates the fp16 feature tile of one 16 x 8
 // block of OUTPUT pixels in shared memory and contracts it against the 7x7x93x64 kernel on the tensor cores
-// (tcgen05.mma, bf16 x bf16 -> fp32 accumulators in tensor memory).  HBM traffic: 12 B per input pixel in,
+// (tcgen05.mma, fp16 x fp16 -> fp32 accumulators in tensor memory).  HBM traffic: 12 B per input pixel in,
 // 256 B per output pixel (= 64 B per input pixel) out -- the kernel is TENSOR-bound (583 kFLOP per output pixel),
-// unlike everything else in this library.  It changes numerics (bf16 operands, like TF's own bf16/TF32 conv
-// paths; fp32 accumulation) and is therefore a separate entry point, never the parity-gated fp32 default.
+// unlike everything else in this library.  It changes numerics (half-precision operands, like TF's own mixed_float16
+// / TF32 conv paths; fp32 accumulation) and is therefore a separate entry point, never the parity-gated fp32 default.
 //
 // Implicit GEMM.  D[m, o] = sum_{ky,kx,c} F(2 oy + ky - pt, 2 ox + kx - pl, c) W[ky,kx,c,o];  m = 128 output pixels
 // (16 rows x 8 columns), N = 64 output channels, K = 49 taps x 96 (93 channels + 3 zero).  For one tap the A operand
 // is a SHIFTED, stride-2 VIEW of the feature tile -- no im2col copy is made.  tcgen05 reads K-major operands as
 // 8-row x 16-byte core matrices addressed by (start, LBO, SBO), so the tile is stored as
-//      [input row ly 0..36][16-byte channel group cg][column parity px][q = lx >> 1][8 channels]     (bf16)
+//      [input row ly 0..36][16-byte channel group cg][column parity px][q = lx >> 1][8 channels]     (fp16)
 // in which the 8 pixels of one output row of the tile are 8 consecutive q (16 B apart) for every tap:
 //      start = buf + ky RP + cg CGP + (kx & 1) PP + (kx >> 1) 16,   LBO = CGP (next channel group),
 //      SBO = 2 RP (next output row = two input rows down).
@@ -23,7 +23,7 @@
 // 51 KB feature buffers, so that the CUDA cores generate one pass while the tensor cores consume the other.
 //
 // Roles of the persistent CTA (one per SM, 20 warps): 13 producer warps (one thread per input pixel of the 37 x 21
-// halo tile: Sobel / votes of the pass, bf16 pack, four 16-byte shared stores), 1 thread streaming the packed weights
+// halo tile: Sobel / votes of the pass, fp16 pack, four 16-byte shared stores), 1 thread streaming the packed weights
 // (one kernel row of one pass = 28 KB per 1-D bulk copy into a 4-stage ring), 2 warps issuing the MMAs (alternating
 // kernel rows, one elected lane, 14 MMAs per row back to back, 294 per tile),
 // 4 epilogue warps (tcgen05.ld of the two partial accumulators, 16 columns at a time, add, scale / shift / ReLU, 256 B per output pixel to
@@ -37,7 +37,7 @@
 // remote arrives, one of its idle threads relays "my half of ring stage s has landed", and the leader's commits are
 // multicast to the barriers of both CTAs.  A pair whose second tile index falls off the end runs a dummy tile there.
 // Inputs with fewer than 4 tiles take the single-CTA kernel (same code, PAIR = false).
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "umma.cuh"
@@ -94,22 +94,24 @@ struct Params {
   int n, h, w, oh, ow, pt, pl, tiles_y, tiles_x, ntiles, relu;
 };
 
+__device__ __forceinline__ float sat_half(float x);
+
 // ------------------------------------------------------------------------------------------ weight packing
 // kernel [7][7][93][64] fp32 (HWIO, what Keras stores) -> for each pass and tap the B operand image tcgen05 reads:
-// K-major no-swizzle core matrices, [16-channel step][K half][8-channel n group][n row][8 k] bf16 (LBO 1024, SBO 128).
+// K-major no-swizzle core matrices, [16-channel step][K half][8-channel n group][n row][8 k] fp16 (LBO 1024, SBO 128).
 // K index k of pass p is feature channel 32 p + k (zero beyond 92).
-__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ kern, __nv_bfloat16* __restrict__ wpk) {
+__global__ void __launch_bounds__(256) k_pack_weights(const float* __restrict__ kern, __half* __restrict__ wpk) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= NPASS * NTAP * KPASS * OC) return;
   const int e = i & 7, r = (i >> 3) & 7, ng = (i >> 6) & 7, kh = (i >> 9) & 1, step = (i >> 10) & 1;
   const int ptap = i >> 11;                    // pass * 49 + tap
   const int tap = ptap % NTAP, pass = ptap / NTAP;
   const int ch = pass * KPASS + step * 16 + kh * 8 + e, o = ng * 8 + r;
-  wpk[i] = __float2bfloat16_rn(ch >= SHDR_FRONTEND_CH ? 0.0f : __ldg(kern + ((size_t)tap * SHDR_FRONTEND_CH + ch) * OC + o));
+  wpk[i] = __float2half_rn(ch >= SHDR_FRONTEND_CH ? 0.0f : sat_half(__ldg(kern + ((size_t)tap * SHDR_FRONTEND_CH + ch) * OC + o)));
 }
 // the same for CTA pairs: [pass][kernel row][half of the output channels][kx][16-channel step][K half][4 n groups][n row][8 k]
 // -- each CTA's share of a kernel row is one contiguous 14 KB block (LBO 512, SBO 128)
-__global__ void __launch_bounds__(256) k_pack_weights_pair(const float* __restrict__ kern, __nv_bfloat16* __restrict__ wpk) {
+__global__ void __launch_bounds__(256) k_pack_weights_pair(const float* __restrict__ kern, __half* __restrict__ wpk) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= NPASS * NTAP * KPASS * OC) return;
   const int e = i & 7, r = (i >> 3) & 7, ng = (i >> 6) & 3, kh = (i >> 8) & 1, step = (i >> 9) & 1;
@@ -118,21 +120,26 @@ __global__ void __launch_bounds__(256) k_pack_weights_pair(const float* __restri
   const int half = rest & 1; rest >>= 1;
   const int ky = rest % 7, pass = rest / 7;
   const int ch = pass * KPASS + step * 16 + kh * 8 + e, o = half * 32 + ng * 8 + r;
-  wpk[i] = __float2bfloat16_rn(ch >= SHDR_FRONTEND_CH ? 0.0f
-                               : __ldg(kern + ((size_t)(ky * 7 + kx) * SHDR_FRONTEND_CH + ch) * OC + o));
+  wpk[i] = __float2half_rn(ch >= SHDR_FRONTEND_CH ? 0.0f
+                           : sat_half(__ldg(kern + ((size_t)(ky * 7 + kx) * SHDR_FRONTEND_CH + ch) * OC + o)));
 }
 
 // ------------------------------------------------------------------------------------------ producers
+// Operands are IEEE half precision (fp16): every feature is in [0, 1] (votes, LDR pixels) or a small multiple of it
+// (Sobel: |.| <= 4), and conv weights are O(1), so fp16's 11-bit significand gives a 4x smaller rounding error than
+// bf16's 8 bits at the same tensor-core rate and the same bytes.  Values beyond fp16's range saturate at +-65504
+// instead of becoming inf (inf x 0 would poison the sum); NaN stays NaN.
+__device__ __forceinline__ float sat_half(float x) { return fabsf(x) > 65504.0f ? copysignf(65504.0f, x) : x; }
 __device__ __forceinline__ unsigned pack2(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  __half2 t = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&t);
 }
 
 // feature channel CH (compile-time after unrolling) of a pixel: the concat order of linearization_net.py:322
 //   0-2 img | 3-8 Sobel (c*2 + {dy, dx}) | 9-20 hist4 | 21-44 hist8 | 45-92 hist16 ((bin-1)*3 + c) | 93-95 zero
 __device__ __forceinline__ float feature(int ch, const float* v, const float* sob) {
-  if (ch < 3) return v[ch];
-  if (ch < 9) return sob[ch - 3];
+  if (ch < 3) return sat_half(v[ch]);
+  if (ch < 9) return sat_half(sob[ch - 3]);
   if (ch < 21) { const int i = ch - 9;  return hist_vote_pow2(v[i % 3], (float)(2 * (i / 3) + 1) / 8.0f, 4.0f); }
   if (ch < 45) { const int i = ch - 21; return hist_vote_pow2(v[i % 3], (float)(2 * (i / 3) + 1) / 16.0f, 8.0f); }
   if (ch < 93) { const int i = ch - 45; return hist_vote_pow2(v[i % 3], (float)(2 * (i / 3) + 1) / 32.0f, 16.0f); }
@@ -157,7 +164,7 @@ __device__ __forceinline__ void gen_pixel(const float* __restrict__ row, int rx,
       const float p00 = q[-RAWP + xm], p01 = q[-RAWP + x0], p02 = q[-RAWP + xp];
       const float p10 = q[xm], p12 = q[xp];
       const float p20 = q[RAWP + xm], p21 = q[RAWP + x0], p22 = q[RAWP + xp];
-      // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to bf16 is the fp32 feature
+      // same tap order as the fp32 front end (frontend.cu), so the value that is rounded to fp16 is the fp32 feature
       float dy = -p00;
       dy = __fadd_rn(dy, -2.0f * p01);
       dy = __fsub_rn(dy, p02);
@@ -345,7 +352,7 @@ __device__ void mma_issuer(const Params& p, unsigned char* fbuf, unsigned char* 
                            uint64_t* wfull, uint64_t* wempty, uint64_t* afull, uint64_t* aempty,
                            uint32_t tmem, unsigned par) {
   using R = Ring<PAIR>;
-  constexpr uint32_t IDESC = idesc_bf16_f32(PAIR ? 256 : 128, OC);
+  constexpr uint32_t IDESC = idesc_f16_f32(PAIR ? 256 : 128, OC);
   const uint64_t ad0 = smem_desc_nosw(smem_u32(fbuf), CGP, SBO_A);
   const uint64_t bd0 = smem_desc_nosw(smem_u32(wbuf), R::LBO, 128);
   const uint32_t a_hi = (uint32_t)(ad0 >> 32), b_hi = (uint32_t)(bd0 >> 32);
@@ -527,10 +534,10 @@ extern "C" int shdr_conv1_pack_weights_f32(const float* kernel_hwio, void* packe
   DeviceGuard g(packed);
   if (g.status != SHDR_OK) return g.status;
   const int total = c1::NPASS * c1::NTAP * c1::KPASS * c1::OC;
-  c1::k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, (__nv_bfloat16*)packed);
+  c1::k_pack_weights<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(kernel_hwio, (__half*)packed);
   SHDR_LAUNCH_CHECK("k_pack_weights");
   c1::k_pack_weights_pair<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      kernel_hwio, (__nv_bfloat16*)((unsigned char*)packed + c1::PACKED_ONE));
+      kernel_hwio, (__half*)((unsigned char*)packed + c1::PACKED_ONE));
   SHDR_LAUNCH_CHECK("k_pack_weights_pair");
   return SHDR_OK;
 }

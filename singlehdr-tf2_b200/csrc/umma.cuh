@@ -26,6 +26,10 @@ __device__ __forceinline__ uint64_t smem_desc_nosw(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// the same for IEEE half precision operands (A / B format 0 = f16)
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread for the whole CTA
 __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -106,7 +106,7 @@ def frontend_host(img, out=None, pool=False, device=0):
 
 def frontend_conv1_host(img, kernel, bias=None, scale=None, relu=False, out=None, device=0):
     """numpy ``[n,h,w,3]`` + conv1's kernel ``[7,7,93,64]`` (and bias / folded-norm scale ``[64]``) -> numpy
-    ``[n, ceil(h/2), ceil(w/2), 64]``: the front end fused into ``crfFeatureNet.conv1`` (tensor cores, bf16 operands).
+    ``[n, ceil(h/2), ceil(w/2), 64]``: the front end fused into ``crfFeatureNet.conv1`` (tensor cores, fp16 operands).
     Per input pixel 12 B go to the device and 64 B come back -- against 372 B for the 93-channel tensor."""
     img = _as_f32(img)
     n, h, w, c = img.shape

@@ -95,7 +95,7 @@ def frontend_bf16(img, stream=None):
 
 def conv1_pack_weights(kernel, stream=None):
     """Pack ``crfFeatureNet.conv1``'s kernel ``[7,7,93,64]`` (fp32 CUDA tensor, HWIO as Keras stores it,
-    linearization_net.py:91) into the bf16 operand image :func:`frontend_conv1` streams through the tensor cores.
+    linearization_net.py:91) into the fp16 operand image :func:`frontend_conv1` streams through the tensor cores.
     Re-pack whenever the variable changes."""
     (bk,) = _dev_inputs(stream, kernel)
     if tuple(bk.shape) != (7, 7, N.FRONTEND_CH, 64):
@@ -108,7 +108,7 @@ def conv1_pack_weights(kernel, stream=None):
 def frontend_conv1(img, packed, bias=None, scale=None, relu=False, stream=None):
     """``crfFeatureNet.conv1(tf.concat([img, edge6, hist4, hist8, hist16], -1))`` in ONE kernel
     (linearization_net.py:312-322 -> :107): ``[n,h,w,3] -> [n, ceil(h/2), ceil(w/2), 64]`` fp32, the 93-channel tensor
-    never touching HBM (tensor cores, bf16 operands, fp32 accumulation -- reduced precision, opt-in).
+    never touching HBM (tensor cores, fp16 operands, fp32 accumulation -- reduced precision, opt-in).
     ``packed`` comes from :func:`conv1_pack_weights`; ``bias [64]`` is conv1's bias; ``scale [64]`` / ``relu`` fold an
     inference-mode ``norm1`` / ``act1`` (:108-109): ``out = act(conv * scale + bias)``."""
     ins = [img, packed] + [a for a in (scale, bias) if a is not None]

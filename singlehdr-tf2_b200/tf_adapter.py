@@ -17,7 +17,7 @@ What ``patch(linearization_net, tf_utils)`` does, in place (no new variables, ch
 * opt-in ``fuse_conv1=True`` (inference only): ``crfFeatureNet.call`` (:101-116) additionally gets the front end
   fused INTO its first layer -- ``conv1`` (7x7/2 'SAME', 93 -> 64, bias), the inference-mode ``norm1`` folded into a
   per-channel scale / shift, and ``act1`` -- as one tensor-core kernel that takes the 3-channel image; the 93-channel
-  tensor never exists.  bf16 operands / fp32 accumulation (reduced precision, like TF's own mixed-precision conv);
+  tensor never exists.  fp16 operands / fp32 accumulation (reduced precision, like TF's own mixed_float16 conv);
   whenever ``training`` is truthy the stock path (fp32 front end + Keras ``conv1``, differentiable) runs instead.
 
 Every replacement carries its gradient through ``tf.custom_gradient`` (kernels in csrc/backward.cu), so the patched

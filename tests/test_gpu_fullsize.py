@@ -138,7 +138,7 @@ def test_config4_frontend_conv1_full(shdr_gpu):
     boxes += [(int(rng.integers(0, 8)), int(rng.integers(8, 200)) * 2, int(rng.integers(8, 200)) * 2) for _ in range(6)]
     for n, y0, x0 in boxes:
         crop = img[n:n + 1, y0:y0 + 96, x0:x0 + 96]
-        ref = oracle.frontend_conv1(crop, kern, bias, bf16_operands=True)          # [1, 48, 48, 64]
+        ref = oracle.frontend_conv1(crop, kern, bias, half_operands=True)          # [1, 48, 48, 64]
         ya, yb = (0 if y0 == 0 else M // 2), (48 if y0 + 96 == 512 else 48 - M // 2)
         xa, xb = (0 if x0 == 0 else M // 2), (48 if x0 + 96 == 512 else 48 - M // 2)
         got = out[n, y0 // 2 + ya:y0 // 2 + yb, x0 // 2 + xa:x0 // 2 + xb]

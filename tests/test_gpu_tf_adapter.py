@@ -274,7 +274,7 @@ def test_patch_fuse_conv1(shdr_gpu, emor, tmp_path, monkeypatch, eager):
         out = net.call(T(img), training=False)
         scale = vec["gamma"] / np.sqrt(vec["var"] + np.float32(1e-3))
         shift = (vec["bias"] - vec["mean"]) * scale + vec["beta"]
-        conv = oracle.frontend_conv1(img, kern, None, bf16_operands=True)
+        conv = oracle.frontend_conv1(img, kern, None, half_operands=True)
         ref_act = np.maximum(conv * scale + shift, 0.0)
         assert "stock_input" not in seen
         assert seen["act1"].shape == (2, 20, 28, 64)

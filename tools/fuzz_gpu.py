@@ -59,7 +59,7 @@ def main():
         kern = (rng.normal(0, 1, (7, 7, 93, 64)) / 67.5).astype(np.float32)
         bias = rng.normal(0, 0.1, 64).astype(np.float32)
         c1 = shdr.frontend_conv1(d, shdr.conv1_pack_weights(D(kern)), bias=D(bias)).numpy()
-        r1 = oracle.frontend_conv1(img, kern, bias, bf16_operands=True)
+        r1 = oracle.frontend_conv1(img, kern, bias, half_operands=True)
         if not np.abs(c1 - r1).max() <= 2e-5 * max(np.abs(r1).max(), 1e-3):
             fails.append(tag + f" conv1 ({np.abs(c1 - r1).max() / np.abs(r1).max():.2e})")
     print(f"{args.cases} random cases x 5 ops in {time.time() - t0:.0f} s: {len(fails)} failures")
