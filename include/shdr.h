@@ -90,6 +90,9 @@ int shdr_frontend_f32(const float* img, float* out, int n, int h, int w,
  * SURVEY.md 8(f) rank 2 for a consumer (crfFeatureNet.conv1, linearization_net.py:91,107) that runs in bf16; it
  * changes numerics and is therefore never what the parity-gated default path or bench.py's headline uses. */
 int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h, int w, void* stream);
+/* the same with IEEE half precision (fp16) instead of bfloat16: 11 instead of 8 significand bits for a consumer that
+ * runs in TensorFlow's mixed_float16 policy; every feature is within +-4, far inside fp16's range. */
+int shdr_frontend_f16(const float* img, void* out_f16, int n, int h, int w, void* stream);
 
 /* ---- front end fused into the input of crfFeatureNet.conv1 --------------
  * Replaces  tf.concat([img, edge6, hist4, hist8, hist16], -1)   (linearization_net.py:322)
@@ -203,6 +206,9 @@ int shdr_dl_sobel6(const struct DLManagedTensor* img, void* stream,
 /* shdr_frontend_bf16 on DLPack tensors: the result is a kDLBfloat / 16-bit tensor [n,h,w,93] */
 int shdr_dl_frontend_bf16(const struct DLManagedTensor* img, void* stream,
                           struct DLManagedTensor** out);
+/* shdr_frontend_f16 on DLPack tensors: the result is a kDLFloat / 16-bit tensor [n,h,w,93] */
+int shdr_dl_frontend_f16(const struct DLManagedTensor* img, void* stream,
+                         struct DLManagedTensor** out);
 int shdr_dl_soft_hist(const struct DLManagedTensor* img, int bins, int pool_k,
                       void* stream, struct DLManagedTensor** out);
 int shdr_dl_invcrf_build(const struct DLManagedTensor* w, int monotone, void* stream,

@@ -10,7 +10,7 @@ from . import _native
 from ._native import ShdrError, device_count, launch_count, require_gpu   # noqa: F401
 from .device import DeviceArray, PinnedArray, Stream, Event, synchronize  # noqa: F401
 from .layers import (                                                      # noqa: F401
-    BINS, POOL_K, sobel_edges6, histogram_layer, frontend, frontend_bf16, hist_multi, conv1_pack_weights, frontend_conv1, parse_invemor,
+    BINS, POOL_K, sobel_edges6, histogram_layer, frontend, frontend_bf16, frontend_f16, hist_multi, conv1_pack_weights, frontend_conv1, parse_invemor,
     set_emor_table, invcrf_pca_w_2_invcrf, invcrf_build, _increase, apply_rf, linearize, linearize_ex, synth_ldr,
     apply_rf_bwd, _increase_bwd, invcrf_build_bwd, frontend_bwd, histogram_layer_bwd,
     AEInvcrfDecodeNet, model,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "shdr_hist_multi_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "shdr_frontend_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "shdr_frontend_bf16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "shdr_frontend_f16": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "shdr_conv1_packed_bytes": (_sz, []),
     "shdr_conv1_pack_weights_f32": (_i, [_vp, _vp, _vp]),
     "shdr_frontend_conv1_f32": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
@@ -66,6 +67,7 @@ SIGNATURES = {
     "shdr_dl_frontend": (_i, [_dl, _i, _vp, _dlp]),
     "shdr_dl_sobel6": (_i, [_dl, _vp, _dlp]),
     "shdr_dl_frontend_bf16": (_i, [_dl, _vp, _dlp]),
+    "shdr_dl_frontend_f16": (_i, [_dl, _vp, _dlp]),
     "shdr_dl_soft_hist": (_i, [_dl, _i, _i, _vp, _dlp]),
     "shdr_dl_invcrf_build": (_i, [_dl, _i, _vp, _dlp]),
     "shdr_dl_increase": (_i, [_dl, _vp, _dlp]),

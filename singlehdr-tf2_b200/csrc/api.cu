@@ -179,7 +179,7 @@ static OwnedTensor* owned_of(DLManagedTensor* t) {
   return (t && t->deleter == owned_deleter) ? static_cast<OwnedTensor*>(t->manager_ctx) : nullptr;
 }
 static int dl_alloc(const int64_t* shape, int ndim, int dev, cudaStream_t st, DLManagedTensor** out,
-                    bool stream_ordered = true, bool bf16 = false) {
+                    bool stream_ordered = true, int half_kind = 0 /* 1: bfloat16, 2: fp16 */) {
   SHDR_REQUIRE(out != nullptr && ndim >= 1 && ndim <= 8, "dl_alloc: bad arguments");
   int64_t numel = 1;
   for (int i = 0; i < ndim; ++i) { SHDR_REQUIRE(shape[i] >= 0, "dl_alloc: negative dim"); numel *= shape[i]; }
@@ -194,7 +194,7 @@ static int dl_alloc(const int64_t* shape, int ndim, int dev, cudaStream_t st, DL
     if (g.status != SHDR_OK) { delete o; return g.status; }
     // stream-ordered allocation from the device's default pool: no implicit device synchronisation, and blocks freed
     // by cudaFree are reused without going back to the driver
-    const size_t bytes = (size_t)(numel > 0 ? numel : 1) * (bf16 ? 2 : sizeof(float));
+    const size_t bytes = (size_t)(numel > 0 ? numel : 1) * (half_kind ? 2 : sizeof(float));
     cudaError_t e = stream_ordered ? cudaMallocAsync(&p, bytes, st) : cudaMalloc(&p, bytes);
     if (e != cudaSuccess) { delete o; return cuda_fail(e, "cudaMalloc(output tensor)"); }
   }
@@ -204,7 +204,7 @@ static int dl_alloc(const int64_t* shape, int ndim, int dev, cudaStream_t st, DL
   t.device.device_type = kDLCUDA;
   t.device.device_id = dev;
   t.ndim = ndim;
-  t.dtype.code = bf16 ? kDLBfloat : kDLFloat; t.dtype.bits = bf16 ? 16 : 32; t.dtype.lanes = 1;
+  t.dtype.code = half_kind == 1 ? kDLBfloat : kDLFloat; t.dtype.bits = half_kind ? 16 : 32; t.dtype.lanes = 1;
   t.shape = o->shape;
   t.strides = nullptr;
   t.byte_offset = 0;
@@ -326,8 +326,20 @@ extern "C" int shdr_dl_frontend_bf16(const struct DLManagedTensor* img, void* st
   DL_TRY(img_dims(v, "frontend_bf16", &n, &h, &w, &c));
   SHDR_REQUIRE(c == 3, "frontend_bf16: img must have 3 channels (got %d)", c);
   int64_t shp[4] = {n, h, w, SHDR_FRONTEND_CH};
-  DL_TRY(dl_alloc(shp, 4, v.dev, (cudaStream_t)stream, out, true, true));
+  DL_TRY(dl_alloc(shp, 4, v.dev, (cudaStream_t)stream, out, true, 1));
   DL_RUN(out, shdr_frontend_bf16(v.p, (*out)->dl_tensor.data, n, h, w, stream));
+  DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
+  return SHDR_OK;
+}
+
+extern "C" int shdr_dl_frontend_f16(const struct DLManagedTensor* img, void* stream, struct DLManagedTensor** out) {
+  View v; int n, h, w, c;
+  DL_TRY(dl_view(img, "frontend_f16", &v));
+  DL_TRY(img_dims(v, "frontend_f16", &n, &h, &w, &c));
+  SHDR_REQUIRE(c == 3, "frontend_f16: img must have 3 channels (got %d)", c);
+  int64_t shp[4] = {n, h, w, SHDR_FRONTEND_CH};
+  DL_TRY(dl_alloc(shp, 4, v.dev, (cudaStream_t)stream, out, true, 2));
+  DL_RUN(out, shdr_frontend_f16(v.p, (*out)->dl_tensor.data, n, h, w, stream));
   DL_RUN(out, dl_mark_ready(*out, (cudaStream_t)stream));
   return SHDR_OK;
 }

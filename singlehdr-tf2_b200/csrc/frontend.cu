@@ -14,6 +14,7 @@
 // as flat, fully coalesced 128-bit stores.  Strips are taken over the flattened pixel index of the
 // whole batch, so strip bases are 16-B aligned for any image width.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -43,7 +44,8 @@ __device__ __forceinline__ void hist_bins_pow2(float v, float* o /* stride 3 bet
 // BF16: the strip is rounded to bfloat16 (round to nearest even) while it is streamed out -- the reduced-precision
 // output flag of SURVEY.md 8(f) rank 2 (halves the 372 B/px write that dominates this kernel's roofline time; changes
 // numerics, so it is a separate entry point and never the parity-gated default).
-template <bool FULL, int HMASK, bool BF16 = false, bool EDGES = false>
+// OUT16: 0 = fp32 output, 1 = bfloat16, 2 = IEEE half precision (fp16)
+template <bool FULL, int HMASK, int OUT16 = 0, bool EDGES = false>
 __global__ void __launch_bounds__(STRIP)
 k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx, int h, int w, int vec_ok) {
   using L = StripLayout<FULL, HMASK, EDGES>;
@@ -106,9 +108,9 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
   // stream the strip out: flat over [pixels in strip] x CH
   const int npx_strip = min(STRIP, npx - p0);
   const int nfl = npx_strip * CH;
-  if (BF16) {
+  if (OUT16) {
     // CHP == CH here (93 is odd); the strip base p0 * CH * 2 bytes is 16-byte aligned (p0 is a multiple of 128)
-    __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out) + (size_t)p0 * CH;
+    unsigned short* ob = reinterpret_cast<unsigned short*>(out) + (size_t)p0 * CH;
     // consecutive lanes read consecutive 128-bit words of the strip (conflict-free) and write 64 bits each
     const int nv = vec_ok ? (nfl >> 2) : 0;               // 4 values in, 2 x bf16x2 out
     const float4* s4 = reinterpret_cast<const float4*>(s);
@@ -116,12 +118,18 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
 #pragma unroll 4
     for (int i = tid; i < nv; i += STRIP) {
       const float4 q = s4[i];
-      __nv_bfloat162 a = __floats2bfloat162_rn(q.x, q.y), b = __floats2bfloat162_rn(q.z, q.w);
       uint2 v;
-      v.x = *reinterpret_cast<unsigned*>(&a); v.y = *reinterpret_cast<unsigned*>(&b);
+      if (OUT16 == 1) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(q.x, q.y), b = __floats2bfloat162_rn(q.z, q.w);
+        v.x = *reinterpret_cast<unsigned*>(&a); v.y = *reinterpret_cast<unsigned*>(&b);
+      } else {
+        __half2 a = __floats2half2_rn(q.x, q.y), b = __floats2half2_rn(q.z, q.w);
+        v.x = *reinterpret_cast<unsigned*>(&a); v.y = *reinterpret_cast<unsigned*>(&b);
+      }
       __stcs(o2 + i, v);
     }
-    for (int i = (nv << 2) + tid; i < nfl; i += STRIP) ob[i] = __float2bfloat16_rn(s[i]);
+    for (int i = (nv << 2) + tid; i < nfl; i += STRIP)
+      ob[i] = OUT16 == 1 ? __bfloat16_as_ushort(__float2bfloat16_rn(s[i])) : __half_as_ushort(__float2half_rn(s[i]));
     return;
   }
   float* og = out + (size_t)p0 * CH;
@@ -146,10 +154,10 @@ k_frontend_strip(const float* __restrict__ img, float* __restrict__ out, int npx
   }
 }
 
-template <bool FULL, int HMASK, bool BF16 = false, bool EDGES = false>
+template <bool FULL, int HMASK, int OUT16 = 0, bool EDGES = false>
 static int launch_strip(const float* img, float* out, long long npx, int h, int w, cudaStream_t st) {
   const unsigned grid = (unsigned)((npx + STRIP - 1) / STRIP);
-  k_frontend_strip<FULL, HMASK, BF16, EDGES><<<grid, STRIP, 0, st>>>(img, out, (int)npx, h, w, aligned16(out) ? 1 : 0);
+  k_frontend_strip<FULL, HMASK, OUT16, EDGES><<<grid, STRIP, 0, st>>>(img, out, (int)npx, h, w, aligned16(out) ? 1 : 0);
   SHDR_LAUNCH_CHECK("k_frontend_strip");
   return SHDR_OK;
 }
@@ -283,7 +291,7 @@ extern "C" int shdr_sobel6_f32(const float* img, float* out, int n, int h, int w
   if (g.status != SHDR_OK) return g.status;
   // the stand-alone RGB tensor takes the strip kernel (edges staged in shared memory, flat 128-bit stores)
   if (c == 3 && out_ch_off == 0 && out_ch_stride == 6)
-    return launch_strip<true, 0, false, true>(img, out, (long long)n * h * w, h, w, (cudaStream_t)stream);
+    return launch_strip<true, 0, 0, true>(img, out, (long long)n * h * w, h, w, (cudaStream_t)stream);
   return launch_sobel_generic(img, out, (long long)n * h * w, h, w, c, out_ch_stride, out_ch_off,
                               (cudaStream_t)stream, g.dev);
 }
@@ -358,5 +366,14 @@ extern "C" int shdr_frontend_bf16(const float* img, void* out_bf16, int n, int h
   SHDR_REQUIRE(h >= 2 && w >= 2, "frontend_bf16: REFLECT padding needs h >= 2 and w >= 2 (got %d x %d)", h, w);
   DeviceGuard g(out_bf16);
   if (g.status != SHDR_OK) return g.status;
-  return launch_strip<true, 7, true>(img, (float*)out_bf16, (long long)n * h * w, h, w, (cudaStream_t)stream);
+  return launch_strip<true, 7, 1>(img, (float*)out_bf16, (long long)n * h * w, h, w, (cudaStream_t)stream);
+}
+
+extern "C" int shdr_frontend_f16(const float* img, void* out_f16, int n, int h, int w, void* stream) {
+  int rc = check_image("frontend_f16", img, (const float*)out_f16, n, h, w, 3);
+  if (rc != SHDR_OK) return rc < 0 ? rc : SHDR_OK;
+  SHDR_REQUIRE(h >= 2 && w >= 2, "frontend_f16: REFLECT padding needs h >= 2 and w >= 2 (got %d x %d)", h, w);
+  DeviceGuard g(out_f16);
+  if (g.status != SHDR_OK) return g.status;
+  return launch_strip<true, 7, 2>(img, (float*)out_f16, (long long)n * h * w, h, w, (cudaStream_t)stream);
 }

@@ -61,14 +61,21 @@ def _itemsize(managed_ptr):
     return int(t.dtype.bits) // 8
 
 
+def _is_float(managed_ptr):
+    """True for kDLFloat tensors (fp32, fp16); False for kDLBfloat."""
+    t = C.cast(managed_ptr, C.POINTER(_DLManagedTensor)).contents.dl_tensor
+    return int(t.dtype.code) == 2
+
+
 class DeviceArray:
-    """A CUDA tensor owned by libshdr (compact row-major): float32, or bfloat16 for the reduced-precision front end
-    (``numpy()`` then returns the 16-bit patterns as ``uint16``)."""
+    """A CUDA tensor owned by libshdr (compact row-major): float32, or a 16-bit type for the reduced-precision front
+    end (``numpy()`` then returns ``float16``, or the bit patterns as ``uint16`` for bfloat16)."""
 
     def __init__(self, managed_ptr):
         self._m = managed_ptr
         self.ptr, self.shape, self.device, _ = _describe(managed_ptr)
         self.itemsize = _itemsize(managed_ptr)
+        self._float = _is_float(managed_ptr)
 
     # -- construction
     @classmethod
@@ -104,7 +111,7 @@ class DeviceArray:
 
     def numpy(self, stream=None):
         self._alive()
-        out = np.empty(self.shape, np.float32 if self.itemsize == 4 else np.uint16)
+        out = np.empty(self.shape, np.float32 if self.itemsize == 4 else (np.float16 if self._float else np.uint16))
         if out.size:
             # the copy stream waits for the producing kernel (whatever stream it ran on)
             N.check(N.lib.shdr_dl_wait_ready(self._m, getattr(stream, "handle", stream), 0))

@@ -131,6 +131,12 @@ def frontend_conv1(img, packed, bias=None, scale=None, relu=False, stream=None):
     return out.mark_ready(stream)
 
 
+def frontend_f16(img, stream=None):
+    """:func:`frontend_bf16` with IEEE half precision (fp16) instead of bfloat16: exactly ``float16(fp32 result)``, for a
+    consumer running in TensorFlow's ``mixed_float16`` policy (``numpy()`` returns ``float16``)."""
+    return _run_dl(N.lib.shdr_dl_frontend_f16, [img], stream=stream)
+
+
 def hist_multi(img, pool=False, stream=None):
     """``concat([hist4, hist8, hist16], -1)`` -> ``[b,h,w,84]`` in one launch."""
     (b,) = _dev_inputs(stream, img)

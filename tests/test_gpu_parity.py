@@ -450,6 +450,16 @@ def test_frontend_bf16_is_the_rounded_fp32_front_end(shdr_gpu, shape):
     assert np.array_equal(got.numpy(), _to_bf16_bits(oracle.frontend(img)))
 
 
+@pytest.mark.parametrize("shape", [(2, 24, 40, 3), (1, 5, 1027, 3)])
+def test_frontend_f16_is_the_rounded_fp32_front_end(shdr_gpu, shape):
+    """the same flag with IEEE half precision: exactly float16(fp32 front end)"""
+    img = rnd(shape, sum(shape) + 6)
+    got = shdr_gpu.frontend_f16(shdr_gpu.DeviceArray.from_numpy(img))
+    assert got.itemsize == 2 and got.shape == shape[:3] + (93,)
+    out = got.numpy()
+    assert out.dtype == np.float16 and np.array_equal(out, oracle.frontend(img).astype(np.float16))
+
+
 @pytest.mark.parametrize("value", [0.0, 1.0, 0.5, 0.125, 0.375, 0.0625, 1.0 / 32.0, 31.0 / 32.0, 0.3])
 def test_pooled_constant_images(shdr_gpu, value):
     """Constant images: at a bin centre every vote of that bin is exactly 1.0, so every interior 16x16 window sums to
