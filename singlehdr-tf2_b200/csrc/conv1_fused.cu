@@ -127,7 +127,8 @@ __global__ void __launch_bounds__(256) k_pack_weights_pair(const float* __restri
 // ------------------------------------------------------------------------------------------ producers
 // Operands are IEEE half precision (fp16): every feature is in [0, 1] (votes, LDR pixels) or a small multiple of it
 // (Sobel: |.| <= 4), and conv weights are O(1), so fp16's 11-bit significand gives a 4x smaller rounding error than
-// bf16's 8 bits at the same tensor-core rate and the same bytes.  Values beyond fp16's range saturate at +-65504
+// bf16's 8 bits at the same tensor-core rate and the same bytes (11 bits is also what TF32 -- TensorFlow's default for
+// fp32 convolutions on Ampere-or-later GPUs -- keeps).  Values beyond fp16's range saturate at +-65504
 // instead of becoming inf (inf x 0 would poison the sum); NaN stays NaN.
 __device__ __forceinline__ float sat_half(float x) { return fabsf(x) > 65504.0f ? copysignf(65504.0f, x) : x; }
 __device__ __forceinline__ unsigned pack2(float lo, float hi) {
