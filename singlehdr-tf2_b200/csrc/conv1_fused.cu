@@ -81,7 +81,8 @@ constexpr size_t PACKED_BYTES = 2 * PACKED_ONE;                // the single-CTA
 constexpr int RAW_R = LR + 2, RAW_C = LC + 2;  // raw fp32 image tile with the Sobel halo: 39 x 23 pixels
 constexpr int RAWC = 24;                  // raw tile, per row and colour: 12 odd columns then 12 even columns (23 used)
 constexpr int RAWP = 3 * RAWC + 15;       // 87 floats per row: consecutive producer lanes (11 even + 10 odd tile columns,
-                                          // then the next row, 87 = 23 (mod 32) words on) read consecutive banks
+                                          // then the next row, 87 = 23 (mod 32) words on) read mostly distinct banks
+                                          // (ncu: still ~2 wavefronts per LDS -- one colliding pair is enough)
 constexpr int RAW_BYTES = ((RAW_R * RAWP * 4 + 15) / 16) * 16;   // 13584
 constexpr int SMEM_BYTES = 2 * FBUF + NWS * WROW + RAW_BYTES;    // 228912 (both modes: Ring::DEPTH * Ring::ROW == NWS * WROW)
 
