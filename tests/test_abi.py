@@ -151,3 +151,19 @@ def test_shard_range_and_tiles():
     assert all(t[2] == max(0, t[0] - 7) and t[3] == min(2160, t[1] + 8) for t in tiles)
     with pytest.raises(ValueError):
         shdr.shard_range(4, 2, 2)
+
+
+def test_sass_of_the_fused_conv1_uses_tcgen05_and_bulk_copies():
+    """The shipped library really drives the 5th-generation tensor cores: the SASS of libshdr.so holds tcgen05 MMAs in
+    CTA-pair form (UTCHMMA.2CTA), multicast commits (UTCBAR), tensor-memory loads (LDTM) and allocation (UTCATOMSWS), and
+    1-D bulk copies (UBLKCP) -- the mnemonics B200_PROFILING.md lists as the proof of tcgen05 / TMA."""
+    import shutil
+    import subprocess
+    from shdr import _native
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _native.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    for mnemonic in ("UTCHMMA.2CTA", "UTCHMMA ", "UTCBAR.2CTA.MULTICAST", "LDTM.x16", "UTCATOMSWS", "UBLKCP.S.G", "SYNCS.ARRIVE.TRANS64"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS of libshdr.so"
+    assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", _native.LIB_PATH], capture_output=True, text=True).stdout
